@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the VCS-h264 interframe hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1], SURVEY 8d "C2"): synthetic 1080p 8-bit 60-frame clip
+(I-P-P-P: 15 I + 45 P), 16x16 macroblocks, +/-16 step-1 full search with the reference's own
+cost (wrapped uint8 difference, motion.py:146) and static test (threshold 2000, motion.py:113),
+motion-compensated residual, 8x8 DCT, quantise QF=50 (rint -> int16 indices), dequantise, IDCT,
+reconstruction.  One "step" = one pass over one such clip per GPU; `value` = frames of all ranks
+/ max-over-ranks device time with the clip resident in HBM; `e2e` = the same through
+vcs_encode_clip_host with pinned HOST buffers (H2D of the clip and D2H of MVs + indices inside
+the timed region).  The same numbers for the generalised true-SAD cost ride along in "sad_mode".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+N > 1: launched by torch.distributed.run, one rank per GPU (weak scaling: one clip per rank, no
+data-path collective; NCCL gathers the per-shard motion vectors at the end of every step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC_NAME = "frames/sec 1080p full-search ME+DCT/quant"
+H, W, T, BS, R, GOP, QF = 1080, 1920, 60, 16, 16, 4, 50.0
+STATIC_THR = 2000
+
+
+def px_ops_per_p_frame(H, W, bs, R):
+    """Algorithmic work of the search: one byte-difference-accumulate per byte of
+    every valid candidate.  1080p/bs16/+-16: 8 590 536 candidates x 768 B = 6.598 G."""
+    def n_axis(dim):
+        return sum(min(p + R, dim - bs) - max(p - R, 0) + 1 for p in range(0, dim - bs + 1, bs))
+    return n_axis(W) * n_axis(H) * 3 * bs * bs
+
+
+def dct_bytes_per_p_frame(H, W, coef_bytes=2, recon=True):
+    """Algorithmic HBM bytes of the residual/DCT/recon kernel per frame: cur 3 + ref 3 + coef
+    3*coef_bytes + recon 3 per pixel (15 B/px with int16 indices)."""
+    return H * W * (3 + 3 + 3 * coef_bytes + (3 if recon else 0))
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_clip(seed):
+    from vcs_h264_b200 import synth
+    return synth.clip(T, H, W, seed=seed)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the CPU port of the reference's algorithm (oracle/vcs_oracle.c; the
+    reference itself is pure Python and /root/reference does not exist on the GPU box), all host
+    threads, same config/metric.  Each step = a bounded sample: the first `sample_frames` frames."""
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    sample_frames = 2 * GOP                                  # 2 I + 6 P at 1080p
+    clip = make_clip(1234)[:sample_frames]
+    prm = orc.symmetric_search_params(R)
+    Q = orc.qtables(QF)
+    cores = orc.max_threads()
+
+    def step():
+        for t in range(sample_frames):
+            if t % GOP:
+                orc.encode_p(clip[t], clip[(t // GOP) * GOP], BS, metric=orc.METRIC_WRAP8,
+                             static_thr=STATIC_THR, Q=Q, round_mode=1, simd=True, nthreads=0, **prm)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    fps = sample_frames * args.steps / dt
+    sample = (f"first {sample_frames} frames ({sample_frames // GOP} I + {sample_frames - sample_frames // GOP} P) "
+              f"of the 60-frame clip per step, C port with SSE2 costs + OpenMP over macroblocks")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC_NAME, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
+        "data": "synthetic", "config": workload_config(),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config():
+    return {"workload": "C2: synthetic 1080p 60-frame clip (15 I + 45 P, I-P-P-P), 16x16 MB, +/-16 step-1 "
+                        "full search, reference cost (wrapped u8 diff) + static test thr 2000, residual, "
+                        "8x8 DCT f64, quant QF50 -> int16 indices, dequant, IDCT, recon",
+            "H": H, "W": W, "frames_per_clip": T, "clips_per_step": "one per GPU", "block": BS, "range": R,
+            "gop": GOP, "qf": QF, "metric": "wrap8", "static_thr": STATIC_THR,
+            "cache": "inputs (373 MB clip) larger than the 126 MB L2; no flush needed",
+            "frames_counted": "all T frames (I-frames are stored, as in encoder.py:41-43)"}
+
+
+def cpu_baseline_sample(seconds_cap=25.0):
+    from oracle import oracle as orc
+    orc.build()
+    clip = make_clip(1234)[:2 * GOP]
+    prm = orc.symmetric_search_params(R)
+    Q = orc.qtables(QF)
+    t0 = time.perf_counter()
+    frames = 0
+    for t in range(2 * GOP):
+        if t % GOP:
+            orc.encode_p(clip[t], clip[(t // GOP) * GOP], BS, metric=orc.METRIC_WRAP8, static_thr=STATIC_THR,
+                         Q=Q, round_mode=1, simd=True, nthreads=0, **prm)
+        frames += 1
+        if time.perf_counter() - t0 > seconds_cap and t % GOP == GOP - 1:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": frames / dt, "unit": "frames/s", "cores": orc.max_threads(), "kind": "port",
+            "sample": f"first {frames} frames of the clip (I-frames free), oracle/vcs_oracle.c with SSE2 costs, "
+                      f"OpenMP over macroblocks, {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import vcs_h264_b200 as v
+    from vcs_h264_b200 import _capi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clip_np = make_clip(1234 + rank)
+    host_in = torch.from_numpy(clip_np).pin_memory()
+    dev_in = host_in.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream(dev)
+    nP = _capi.num_p_frames(T, GOP)
+    N = _capi.num_blocks(H, W, BS)
+
+    def measure(metric):
+        ce = v.ClipEncoder([H, W], block_size=BS, search="full", search_range=R, gop_len=GOP, qf=QF,
+                           metric=metric, static_thr=STATIC_THR, coef_mode=v.COEF_I16_RINT, device=local_rank)
+        ctx = ce.ctx
+        dout = ce.alloc_device_outputs(T, want_coef=True, want_recon=True)
+        gather = [torch.empty_like(dout["mv"]) for _ in range(world)] if dist is not None else None
+
+        def step():
+            ce.encode_device(dev_in, dout, stream)
+            if gather is not None:                       # per-shard results -> every rank (NCCL)
+                dist.all_gather(gather, dout["mv"])
+
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        ctx.enable_kernel_timing(True)
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = ctx.launch_count() - l0
+        me_ms, dct_ms, ncalls = ctx.kernel_times()
+        ctx.enable_kernel_timing(False)
+        static_frac = float((dout["flags"] & 1).float().mean().item())
+
+        # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------
+        hout = ce.alloc_host_outputs(T, want_coef=True, want_recon=False, pinned=True)
+        for _ in range(max(1, args.warmup)):
+            ce.encode_host(host_in, hout)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ce.encode_host(host_in, hout)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        if dist is not None:
+            dist.barrier()
+        same = bool(torch.equal(hout["mv"], dout["mv"].cpu()) and torch.equal(hout["coef"], dout["coef"].cpu()))
+        h2d = host_in.numel()
+        d2h = sum(hout[k].numel() * hout[k].element_size() for k in ("mv", "cost", "flags", "coef"))
+        return dict(ms=ms, launches=launches, me_ms=me_ms / max(ncalls, 1), dct_ms=dct_ms / max(ncalls, 1),
+                    e2e_fps=world * T * args.steps / dt, e2e_ms=1e3 * dt / args.steps, h2d=h2d, d2h=d2h,
+                    clocks=clocks, static_frac=static_frac, host_equals_device=same)
+
+    ctx0 = v.runtime.get_context(local_rank)
+    ctx0.set_stream(stream.cuda_stream)
+    mb = {}
+    if rank == 0:
+        for which, name in ((0, "vabsdiff4_acc"), (1, "iadd3"), (2, "lop3"), (3, "imad"), (4, "idp4a"),
+                            (5, "wrap8_triple_words"), (6, "vabsdiff4_with_lds")):
+            rate, mhz = ctx0.microbench(which, 4000)
+            mb[name] = {"warp_instr_per_s": rate, "sm_mhz": mhz,
+                        "per_clk_per_sm": rate / (mhz * 1e6) / ctx0.device_info()["sm_count"]}
+    wrap = measure(_capi.METRIC_WRAP8)
+    sad = measure(_capi.METRIC_SAD) if not args.skip_sad else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    pxops = px_ops_per_p_frame(H, W, BS, R) * nP           # per ME launch (one clip)
+    peak_pxops = mb["vabsdiff4_acc"]["warp_instr_per_s"] * 32 * 4
+
+    def me_roof(m):
+        ach = pxops / (m["me_ms"] * 1e-3)
+        return {"bound": "int32", "kernel": "me search (one launch = 45 P-frames)", "achieved": ach / 1e9,
+                "peak": peak_pxops / 1e9, "unit": "Gpxop/s", "frac": ach / peak_pxops, "traffic": None,
+                "ms_per_launch": m["me_ms"],
+                "peak_source": "VABSDIFF4.U8.ACC issue rate measured in this run x 32 lanes x 4 bytes"}
+
+    def dct_roof(m):
+        b = dct_bytes_per_p_frame(H, W) * nP
+        ach = b / (m["dct_ms"] * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "dct_stage_kernel (one launch = 45 P-frames)", "achieved": ach,
+                "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "ms_per_launch": m["dct_ms"], "peak_source": hbm_src}
+
+    line = {
+        "metric": METRIC_NAME, "value": world * T * args.steps / (wrap["ms"] * 1e-3), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wrap["ms"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+        "config": workload_config(), "clocks": wrap["clocks"],
+        "e2e": {"value": wrap["e2e_fps"], "unit": "frames/s", "h2d_bytes_per_step": wrap["h2d"],
+                "d2h_bytes_per_step": wrap["d2h"], "ms_per_step": wrap["e2e_ms"],
+                "host_equals_device": wrap["host_equals_device"]},
+        "gpu_launches": wrap["launches"],
+        "roofline": me_roof(wrap), "roofline_dct": dct_roof(wrap),
+        "static_fraction": wrap["static_frac"], "microbench": mb,
+    }
+    if sad is not None:
+        line["sad_mode"] = {"value": world * T * args.steps / (sad["ms"] * 1e-3), "unit": "frames/s",
+                            "ms_per_step": sad["ms"] / args.steps, "e2e": sad["e2e_fps"],
+                            "roofline": me_roof(sad), "clocks": sad["clocks"]}
+    if world == 1 and not args.skip_cpu:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-sad", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

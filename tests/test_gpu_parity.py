@@ -1,0 +1,276 @@
+"""Parity of the CUDA path (through the C ABI) against the reference's golden vectors and the
+CPU oracle.  Integer outputs (MVs, costs, flags, pixels, quantised indices) and the float64
+coefficient planes must be bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vcs():
+    import vcs_h264_b200 as v
+    v.runtime.get_context()          # fails loudly without a GPU / the built extension
+    return v
+
+
+def _gpu_me(vcs, cur, ref, bs, lo, hi, step, slack, metric=0, static_thr=2000, kernel=0):
+    c = vcs._capi
+    H, W = cur.shape[:2]
+    p = c.me_reference_params(H, W, bs)
+    p.lo, p.hi, p.step, p.slack, p.metric, p.static_thr, p.kernel = lo, hi, step, slack, metric, static_thr, kernel
+    N = c.num_blocks(H, W, bs)
+    mv = np.empty((N, 2), np.int16); cost = np.empty(N, np.uint32); flags = np.empty(N, np.uint8)
+    ctx = vcs.runtime.get_context()
+    cur = np.ascontiguousarray(cur); ref = np.ascontiguousarray(ref)
+    ctx.call("vcs_me_search_host", p, cur.ctypes.data, ref.ctypes.data, mv.ctypes.data,
+             cost.ctypes.data, flags.ctypes.data)
+    return mv.astype(np.int32), cost, flags
+
+
+def test_me_golden_cases(vcs, orc, golden, golden_meta):
+    """Every golden ME case of the unmodified reference (motion.py:20-36), both kernels."""
+    for case in golden_meta["me_cases"]:
+        n, bs = case["name"], case["bs"]
+        cur, ref = golden[f"me_{n}_cur"], golden[f"me_{n}_ref"]
+        prm = orc.reference_search_params(bs, R=case["R"], step=1 if case["step1"] else None)
+        for kernel in (vcs.ME_GENERIC, vcs.ME_AUTO):
+            mv, cost, flags = _gpu_me(vcs, cur, ref, bs, kernel=kernel, **prm)
+            assert np.array_equal(mv, golden[f"me_{n}_mv"]), (n, kernel)
+            assert np.array_equal(flags & 1, golden[f"me_{n}_static"]), (n, kernel)
+            gc = golden[f"me_{n}_cost"]
+            ok = gc >= 0
+            assert np.array_equal(cost[ok].astype(np.int64), gc[ok]), (n, kernel)
+            assert np.all(flags[~ok] == 2), (n, kernel)
+            omv, ocost, oflags = orc.me(cur, ref, bs, **prm)
+            assert np.array_equal(cost, ocost) and np.array_equal(flags, oflags)
+
+
+@pytest.mark.parametrize("bs,R", [(16, 16), (16, 8), (8, 8), (8, 16), (16, 32), (4, 4)])
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("thr", [2000, -1])
+def test_full_search_vs_oracle(vcs, orc, bs, R, metric, thr):
+    """Symmetric +/-R step-1 search (BASELINE configs 2/3/5) on seeded frames, incl. frame-edge
+    clipping, vs the oracle restatement; MVs, costs and flags bit-exact."""
+    from vcs_h264_b200 import synth
+    H, W = (112, 176) if bs >= 8 else (40, 56)
+    clip = synth.clip(3, H, W, seed=bs * 100 + R, noise=2, margin=48)
+    rng = np.random.default_rng(R)
+    cur, ref = clip[2].copy(), clip[0]
+    cur[:bs * 2, :bs * 3] = ref[:bs * 2, :bs * 3]            # some static macroblocks
+    cur[-bs:, -bs * 2:] = rng.integers(0, 256, (bs, bs * 2, 3), dtype=np.uint8)
+    prm = orc.symmetric_search_params(R)
+    omv, ocost, oflags = orc.me(cur, ref, bs, metric=metric, static_thr=thr, **prm)
+    for kernel in (vcs.ME_GENERIC, vcs.ME_AUTO):
+        mv, cost, flags = _gpu_me(vcs, cur, ref, bs, metric=metric, static_thr=thr, kernel=kernel, **prm)
+        assert np.array_equal(mv, omv), kernel
+        assert np.array_equal(cost, ocost), kernel
+        assert np.array_equal(flags, oflags), kernel
+
+
+def test_ties_first_minimum_wins(vcs, orc):
+    """Flat and periodic frames: many exact ties; scan order rows-outer/cols-inner, strict '<'
+    (motion.py:133-152) must pick the same candidate as the oracle."""
+    yy, xx = np.mgrid[0:96, 0:160]
+    per = (((xx % 4) * 50 + (yy % 2) * 30) % 256).astype(np.uint8)
+    ref = np.stack([per, per, per], -1)
+    cur = np.roll(ref, (2, 4), (0, 1)).copy()
+    flat_r = np.full((96, 160, 3), 7, np.uint8); flat_c = np.full((96, 160, 3), 200, np.uint8)
+    for c_, r_ in ((cur, ref), (flat_c, flat_r), (flat_r, flat_c)):
+        for metric in (0, 1):
+            for bs, R in ((16, 16), (8, 8)):
+                prm = orc.symmetric_search_params(R)
+                omv, ocost, ofl = orc.me(c_, r_, bs, metric=metric, static_thr=-1, **prm)
+                for kernel in (vcs.ME_GENERIC, vcs.ME_AUTO):
+                    mv, cost, fl = _gpu_me(vcs, c_, r_, bs, metric=metric, static_thr=-1, kernel=kernel, **prm)
+                    assert np.array_equal(mv, omv) and np.array_equal(cost, ocost)
+
+
+def test_p_frame_pipeline_golden(vcs, golden, golden_meta):
+    """encoder.py:49-70 + decoder.py:52-69 through the drop-in classes, stage by stage, against
+    the reference's own outputs (float64 planes bit-exact)."""
+    for case in golden_meta["pf_cases"]:
+        n, bs = case["name"], case["bs"]
+        cur, ref = golden[f"pf_{n}_cur"], golden[f"pf_{n}_ref"]
+        H, W = cur.shape[:2]
+        mp = vcs.MotionProcessor(bs, [H, W])
+        dc = vcs.DCTCompressor(8)
+        mvs, coords = mp.process_motion_prediction(cur, ref)
+        assert isinstance(mvs, list) and isinstance(mvs[0][0], int)
+        assert np.array_equal(np.array(mvs), golden[f"pf_{n}_mv"])
+        pred = mp.reconstruct_from_motion_vectors(mvs, ref, coords)
+        assert np.array_equal(pred, golden[f"pf_{n}_pred"])
+        resid = mp.get_residuals(input_frame=cur, reconstructed=pred)
+        assert np.array_equal(resid, golden[f"pf_{n}_resid"])
+        planes = dc.compress(resid)
+        assert len(planes) == 3 and planes[0].dtype == np.float64
+        assert np.array_equal(np.stack(planes), golden[f"pf_{n}_planes"])
+        dec = dc.decompress(compressed=planes, imshape=pred.shape)
+        assert np.array_equal(dec, golden[f"pf_{n}_dec"])
+        assert np.array_equal(mp._add(pred, dec), golden[f"pf_{n}_final"])
+        planes_r = dc.compress(resid, rounded=True)
+        assert np.array_equal(np.stack(planes_r), golden[f"pf_{n}_planes_r"])
+        assert np.array_equal(dc.decompress(planes_r, pred.shape, pred=pred), golden[f"pf_{n}_final_r"])
+        idx = dc.compress_indices(resid)
+        assert np.array_equal(idx.astype(np.float64), golden[f"pf_{n}_planes_r"])
+        assert np.array_equal(dc.decompress(list(idx), pred.shape), golden[f"pf_{n}_dec_r"])
+
+
+@pytest.mark.parametrize("qf", [10, 50, 99])
+def test_stills_quality_sweep(vcs, golden, golden_meta, qf):
+    """DCTCompression/dct.py:169-208 at QF 10/50/99."""
+    from vcs_h264_b200.DCTcompressor import quality_tables
+    img = golden["still_img"]
+    dc = vcs.DCTCompressor(8)
+    dc.Q = quality_tables(qf)
+    planes = dc.compress(img)
+    assert np.array_equal(np.stack(planes), golden[f"still_q{qf}_planes"])
+    pr = dc.compress(img, rounded=True)
+    assert np.array_equal(dc.decompress(pr, img.shape), golden[f"still_q{qf}_dec"])
+    sparsity = 1.0 - np.count_nonzero(np.stack(pr)) / np.stack(pr).size
+    assert sparsity == golden_meta[f"still_q{qf}_sparsity"]
+
+
+def test_encoder_decoder_dropin(vcs, orc):
+    """main.py's loop on a small synthetic clip: Encoder/Decoder drop-ins vs the oracle."""
+    from vcs_h264_b200 import synth
+    clip = synth.clip(6, 64, 96, seed=5, margin=32)
+    enc = vcs.Encoder(pattern=["I", "P", "P", "P"], shape=[64, 96], block_size=8, with_DCT=True)
+    for n, f in enumerate(clip):
+        enc.encode_frame(f, n)
+    assert [f.t for f in enc.encoded_frames] == ["I", "P", "P", "P", "I", "P"]
+    dec = vcs.Decoder(encoded_frames=enc.encoded_frames, fps=25.0, shape=[64, 96],
+                      ref_frames=enc.ref_frames, block_size=8, with_DCT=True)
+    frames = dec.decode_frames(with_residuals=True)
+    prm = orc.reference_search_params(8)
+    for n, f in enumerate(clip):
+        if n % 4 == 0:
+            assert np.array_equal(frames[n], f)
+            continue
+        o = orc.encode_p(f, clip[(n // 4) * 4], 8, **prm)
+        fr = enc.encoded_frames[n]
+        assert np.array_equal(np.array(fr.mv), o["mv"])
+        assert np.array_equal(np.stack(fr.r), o["planes"])
+        assert np.array_equal(frames[n], o["recon"])
+        assert fr.ref_i == n // 4 and fr.i == n
+
+
+@pytest.mark.parametrize("coef_mode", [0, 1, 2])
+def test_clip_api_host_and_device(vcs, orc, coef_mode):
+    """Whole-clip C-ABI calls (host buffers and device tensors) vs per-frame oracle."""
+    import torch
+    from vcs_h264_b200 import synth
+    T, H, W, bs, R = 10, 64, 96, 16, 8
+    clip = synth.clip(T, H, W, seed=77, margin=32)
+    clip[5, :32, :48] = clip[4, :32, :48]                     # static blocks in one P-frame
+    ce = vcs.ClipEncoder([H, W], block_size=bs, search="full", search_range=R, gop_len=4,
+                         coef_mode=coef_mode)
+    out = ce.encode_host(clip, want_coef=True, want_recon=True)
+    dev_in = torch.from_numpy(clip).cuda()
+    dout = ce.alloc_device_outputs(T)
+    ce.encode_device(dev_in, dout)
+    torch.cuda.synchronize()
+    prm = orc.symmetric_search_params(R)
+    for p, t in enumerate(ce.p_frame_indices(T)):
+        o = orc.encode_p(clip[t], clip[(t // 4) * 4], bs, round_mode=int(coef_mode != 0), **prm)
+        for res in (out, {k: v.cpu() for k, v in dout.items()}):
+            assert np.array_equal(np.asarray(res["mv"][p]).astype(np.int32), o["mv"])
+            assert np.array_equal(np.asarray(res["cost"][p]).view(np.uint32), o["cost"])
+            assert np.array_equal(np.asarray(res["flags"][p]), o["flags"])
+            assert np.array_equal(np.asarray(res["coef"][p]).astype(np.float64), o["planes"])
+            assert np.array_equal(np.asarray(res["recon"][p]), o["recon"])
+
+
+def test_reference_search_clip(vcs, orc):
+    """ClipEncoder(search='reference') == MotionProcessor defaults on every P-frame."""
+    from vcs_h264_b200 import synth
+    T, H, W = 7, 72, 104
+    clip = synth.clip(T, H, W, seed=9, margin=32)
+    for bs in (8, 16):
+        ce = vcs.ClipEncoder([H, W], block_size=bs, search="reference", gop_len=4, coef_mode=0)
+        out = ce.encode_host(clip, want_coef=True, want_recon=True)
+        prm = orc.reference_search_params(bs)
+        for p, t in enumerate(ce.p_frame_indices(T)):
+            o = orc.encode_p(clip[t], clip[(t // 4) * 4], bs, **prm)
+            assert np.array_equal(np.asarray(out["mv"][p]).astype(np.int32), o["mv"])
+            assert np.array_equal(np.asarray(out["coef"][p]), o["planes"])
+            assert np.array_equal(np.asarray(out["recon"][p]), o["recon"])
+
+
+def test_full_size_properties_1080p(vcs, orc):
+    """BASELINE config 2 geometry (1080p, bs 16, +/-16): size-independent properties.
+    (i) planted global shift is found exactly under SAD with zero cost away from the borders;
+    (ii) un-rounded DCT->IDCT is the identity up to the truncating store: |recon - cur| <= 1;
+    (iii) a strip of the frame agrees bit-exactly with the oracle."""
+    import torch
+    from vcs_h264_b200 import synth
+    H, W, bs, R = 1080, 1920, 16, 16
+    base = synth.texture(H, W, seed=3, margin=32)
+    ref = np.ascontiguousarray(base[32:32 + H, 32:32 + W])
+    cur = np.ascontiguousarray(base[32 + 5:32 + 5 + H, 32 - 9:32 - 9 + W])   # cur(y,x)=ref(y+5,x-9)
+    clip = np.stack([ref, cur])
+    ce = vcs.ClipEncoder([H, W], block_size=bs, search="full", search_range=R, gop_len=2,
+                         metric=vcs.METRIC_SAD, static_thr=-1, coef_mode=0)
+    out = ce.encode_host(clip, want_coef=True, want_recon=True)
+    mv = np.asarray(out["mv"][0]).astype(np.int32).reshape(H // bs, W // bs, 2)
+    cost = np.asarray(out["cost"][0]).view(np.uint32).reshape(H // bs, W // bs)
+    inner = (slice(0, (H - 5 - bs) // bs), slice(1, None))
+    assert np.all(mv[inner] == [-9, 5]) and np.all(cost[inner] == 0)
+    recon = np.asarray(out["recon"][0]).astype(np.int16)
+    d = np.abs(((recon - cur.astype(np.int16) + 128) % 256) - 128)
+    assert d.max() <= 1
+    # (iii) oracle on a strip: rows 0..95 see candidates only inside rows 0..127
+    strip = 96
+    ce2 = vcs.ClipEncoder([H, W], block_size=bs, search="full", search_range=R, gop_len=2, coef_mode=2)
+    rng = np.random.default_rng(0)
+    cur2 = np.clip(cur.astype(np.int16) + rng.integers(-2, 3, cur.shape), 0, 255).astype(np.uint8)
+    out2 = ce2.encode_host(np.stack([ref, cur2]), want_coef=True, want_recon=True)
+    o = orc.encode_p(cur2[:strip + 32], ref[:strip + 32], bs, round_mode=1,
+                     **orc.symmetric_search_params(R))
+    nrow = strip // bs
+    nbx = W // bs
+    assert np.array_equal(np.asarray(out2["mv"][0]).astype(np.int32)[:nrow * nbx], o["mv"][:nrow * nbx])
+    assert np.array_equal(np.asarray(out2["cost"][0]).view(np.uint32)[:nrow * nbx], o["cost"][:nrow * nbx])
+    assert np.array_equal(np.asarray(out2["coef"][0])[:, :strip].astype(np.float64), o["planes"][:, :strip])
+    assert np.array_equal(np.asarray(out2["recon"][0])[:strip], o["recon"][:strip])
+
+
+def test_shards_equal_single(vcs):
+    """N GOP shards == 1 shard, bit for bit."""
+    from vcs_h264_b200 import sharding, synth
+    T, H, W = 18, 64, 96
+    clip = synth.clip(T, H, W, seed=21, margin=32)
+    ce = vcs.ClipEncoder([H, W], block_size=16, search="full", search_range=8, gop_len=4)
+    whole = ce.encode_host(clip, want_coef=True, want_recon=True)
+    for world in (2, 3, 4):
+        parts = {k: [] for k in whole}
+        for r in range(world):
+            t0, t1 = sharding.frame_range(T, 4, r, world)
+            if t1 > t0:
+                o = ce.encode_host(np.ascontiguousarray(clip[t0:t1]), want_coef=True, want_recon=True)
+                for k in whole:
+                    parts[k].append(np.asarray(o[k]))
+        for k in whole:
+            assert np.array_equal(np.concatenate(parts[k], 0), np.asarray(whole[k])), (k, world)
+
+
+def test_error_behaviour(vcs):
+    c = vcs._capi
+    ctx = vcs.runtime.get_context()
+    with pytest.raises(ValueError):                      # reference: broadcast error for bs != 8
+        vcs.DCTCompressor(16).compress(np.zeros((16, 16, 3), np.uint8))
+    with pytest.raises(ValueError):                      # sides not multiples of 8
+        vcs.DCTCompressor(8).compress(np.zeros((12, 16, 3), np.uint8))
+    p = c.me_reference_params(64, 64, 8)
+    p.step = 0
+    buf = np.zeros((64, 64, 3), np.uint8)
+    mv = np.zeros((64, 2), np.int16)
+    with pytest.raises(c.VcsError):
+        ctx.call("vcs_me_search_host", p, buf.ctypes.data, buf.ctypes.data, mv.ctypes.data, None, None)
+    p = c.me_reference_params(64, 64, 8)
+    p.kernel = c.ME_TILED                                # step 3: tiled kernel must refuse, not fall back
+    with pytest.raises(c.VcsError):
+        ctx.call("vcs_me_search_host", p, buf.ctypes.data, buf.ctypes.data, mv.ctypes.data, None, None)
+    mp = vcs.MotionProcessor(8, [64, 64])
+    with pytest.raises(c.VcsError):                      # MV pointing outside the frame
+        mp.reconstruct_from_motion_vectors([[-100, 0]] * 64, buf, mp._block_coords().tolist())

@@ -1,0 +1,124 @@
+"""Clip-level (batched) front-end of the hot path.
+
+The reference encodes one frame per Python call (main.py:34-41).  At kfps rates the per-frame
+list marshalling would dominate, so this module exposes the same pipeline -- Encoder's GOP rule
+(encoder.py:25,51-52), MotionProcessor search, residual, DCTCompressor quantiser and the decoder's
+reconstruction -- over a whole clip in one C-ABI call, with array outputs indexed by P-frame
+ordinal.  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _capi
+from .runtime import get_context
+
+COEF_DTYPES = {_capi.COEF_F64: np.float64, _capi.COEF_F64_RINT: np.float64,
+               _capi.COEF_I16_RINT: np.int16}
+
+
+class ClipEncoder:
+    """ME (+ static test) -> MC -> residual -> 8x8 DCT -> quantise [-> dequantise -> IDCT ->
+    reconstruct] for every P-frame of a clip.
+
+    search: "reference" = MotionProcessor's own window/step (motion.py:123-140);
+            "full"      = symmetric +/-search_range, step 1 (BASELINE.json configs 2/3/5).
+    """
+
+    def __init__(self, shape, block_size=16, search="full", search_range=16, gop_len=4, qf=50.0,
+                 metric=_capi.METRIC_WRAP8, static_thr=2000, coef_mode=_capi.COEF_I16_RINT,
+                 kernel=_capi.ME_AUTO, device=0):
+        H, W = int(shape[0]), int(shape[1])
+        if search == "reference":
+            self.params = _capi.me_reference_params(H, W, block_size)
+            self.params.metric = metric
+            self.params.static_thr = static_thr
+        elif search == "full":
+            self.params = _capi.me_fullsearch_params(H, W, block_size, search_range, metric, static_thr)
+        else:
+            raise ValueError("search must be 'reference' or 'full'")
+        self.params.kernel = kernel
+        if gop_len < 2:
+            raise ValueError("gop_len must be >= 2 (pattern of one I-frame + P-frames)")
+        self.H, self.W, self.bs, self.gop_len = H, W, block_size, gop_len
+        self.N = _capi.num_blocks(H, W, block_size)
+        self.coef_mode = coef_mode
+        self.device = device
+        self.ctx = get_context(device)
+        self.Q = _capi.q_tables(qf)
+        self.ctx.set_q(self.Q)
+
+    def num_p_frames(self, T):
+        return _capi.num_p_frames(T, self.gop_len)
+
+    def p_frame_indices(self, T):
+        return [t for t in range(T) if t % self.gop_len != 0]
+
+    # -- host buffers in, host buffers out (bench.py e2e; copies inside) -----------------------
+    def alloc_host_outputs(self, T, want_coef=True, want_recon=False, pinned=True):
+        import torch
+        nP = self.num_p_frames(T)
+
+        def buf(shape, dtype):
+            t = torch.empty(shape, dtype=dtype)
+            return t.pin_memory() if pinned and torch.cuda.is_available() else t
+        out = dict(mv=buf((nP, self.N, 2), torch.int16), cost=buf((nP, self.N), torch.int32),
+                   flags=buf((nP, self.N), torch.uint8))
+        if want_coef:
+            dt = torch.int16 if self.coef_mode == _capi.COEF_I16_RINT else torch.float64
+            out["coef"] = buf((nP, 3, self.H, self.W), dt)
+        if want_recon:
+            out["recon"] = buf((nP, self.H, self.W, 3), torch.uint8)
+        return out
+
+    def encode_host(self, frames, out=None, want_coef=True, want_recon=False):
+        """frames: uint8 [T,H,W,3] numpy array or (pinned) CPU torch tensor."""
+        T = int(frames.shape[0])
+        if tuple(frames.shape[1:]) != (self.H, self.W, 3):
+            raise ValueError(f"frames must be [T,{self.H},{self.W},3] uint8")
+        if out is None:
+            out = self.alloc_host_outputs(T, want_coef, want_recon, pinned=False)
+        self.ctx.set_q(self.Q)
+        self.ctx.call("vcs_encode_clip_host", self.params, _capi.ptr(frames), T, self.gop_len,
+                      self.coef_mode, _capi.ptr(out["mv"]), _capi.ptr(out.get("cost")),
+                      _capi.ptr(out.get("flags")), _capi.ptr(out.get("coef")),
+                      _capi.ptr(out.get("recon")))
+        return out
+
+    # -- device resident (bench.py value) --------------------------------------------------------
+    def alloc_device_outputs(self, T, want_coef=True, want_recon=True):
+        import torch
+        nP = self.num_p_frames(T)
+        dev = torch.device("cuda", self.device)
+        out = dict(mv=torch.empty((nP, self.N, 2), dtype=torch.int16, device=dev),
+                   cost=torch.empty((nP, self.N), dtype=torch.int32, device=dev),
+                   flags=torch.empty((nP, self.N), dtype=torch.uint8, device=dev))
+        if want_coef:
+            dt = torch.int16 if self.coef_mode == _capi.COEF_I16_RINT else torch.float64
+            out["coef"] = torch.empty((nP, 3, self.H, self.W), dtype=dt, device=dev)
+        if want_recon:
+            out["recon"] = torch.empty((nP, self.H, self.W, 3), dtype=torch.uint8, device=dev)
+        return out
+
+    def encode_device(self, frames_dev, out, stream=None):
+        """frames_dev: uint8 CUDA tensor [T,H,W,3]; kernels are enqueued on `stream`
+        (default: torch's current stream) and not synchronised."""
+        import torch
+        T = int(frames_dev.shape[0])
+        s = stream if stream is not None else torch.cuda.current_stream(frames_dev.device)
+        self.ctx.set_stream(s.cuda_stream)
+        self.ctx.call("vcs_encode_clip_dev", self.params, _capi.ptr(frames_dev), T, self.gop_len,
+                      self.coef_mode, _capi.ptr(out["mv"]), _capi.ptr(out.get("cost")),
+                      _capi.ptr(out.get("flags")), _capi.ptr(out.get("coef")),
+                      _capi.ptr(out.get("recon")))
+        return out
+
+    def me_device(self, frames_dev, out, stream=None):
+        """Search only (BASELINE config 5's ME-only sweep)."""
+        import torch
+        T = int(frames_dev.shape[0])
+        s = stream if stream is not None else torch.cuda.current_stream(frames_dev.device)
+        self.ctx.set_stream(s.cuda_stream)
+        self.ctx.call("vcs_me_search_clip_dev", self.params, _capi.ptr(frames_dev), T, self.gop_len,
+                      _capi.ptr(out["mv"]), _capi.ptr(out.get("cost")), _capi.ptr(out.get("flags")))
+        return out

@@ -1,0 +1,711 @@
+// vcs_b200.cu -- C ABI (include/vcs_b200.h) of the B200-native VCS-h264 interframe hot path.
+//
+// Host side only: argument checking, device/pinned scratch, stream plumbing and kernel
+// launches.  All arithmetic lives in the kernels (me_generic.cuh, me_tiled.cuh,
+// dct_stage.cuh).  There is no CPU fallback anywhere in this library.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/vcs_b200.h"
+#include "common.cuh"
+#include "dct_stage.cuh"
+#include "me_generic.cuh"
+#include "me_tiled.cuh"
+#include "microbench.cuh"
+
+using namespace vcs;
+
+namespace {
+
+constexpr int NUM_DEV_SLOTS = 12;
+enum DevSlot { S_FRAMES = 0, S_MV, S_COST, S_FLAGS, S_COEF, S_RECON, S_AUX0, S_AUX1, S_AUX2, S_MB, S_CYC };
+
+struct EvTriple {
+    cudaEvent_t e0, e1, e2;
+    bool has_me, has_dct;
+};
+
+}  // namespace
+
+struct vcs_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    char err[512] = {0};
+    double h_Q[192];
+    double *d_Q = nullptr;
+    int64_t launches = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;
+    void *dev[NUM_DEV_SLOTS] = {nullptr};
+    size_t dev_cap[NUM_DEV_SLOTS] = {0};
+    std::vector<cudaEvent_t> chunk_events;
+    bool timing = false;
+    std::vector<EvTriple> ev_pool;
+    size_t ev_used = 0;
+    MeTiledState tiled;
+};
+
+namespace {
+
+int fail(vcs_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CK(ctx, call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(ctx, VCS_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,          \
+                        cudaGetErrorString(e__));                                              \
+    } while (0)
+
+int dev_buf(vcs_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes > ctx->dev_cap[slot]) {
+        if (ctx->dev[slot]) {
+            CK(ctx, cudaDeviceSynchronize());
+            CK(ctx, cudaFree(ctx->dev[slot]));
+            ctx->dev[slot] = nullptr;
+            ctx->dev_cap[slot] = 0;
+        }
+        size_t cap = (bytes + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&ctx->dev[slot], cap);
+        if (e != cudaSuccess)
+            return fail(ctx, VCS_E_NOMEM, "cudaMalloc(%zu) -> %s", cap, cudaGetErrorString(e));
+        ctx->dev_cap[slot] = cap;
+    }
+    *out = ctx->dev[slot];
+    return VCS_OK;
+}
+
+int check_me_params(vcs_ctx *ctx, const vcs_me_params *p) {
+    if (!p) return fail(ctx, VCS_E_INVALID, "params is NULL");
+    if (p->bs <= 0 || p->step <= 0 || p->H < p->bs || p->W < p->bs || p->slack < 0)
+        return fail(ctx, VCS_E_INVALID, "bad ME geometry H=%d W=%d bs=%d step=%d", p->H, p->W,
+                    p->bs, p->step);
+    if (p->metric != VCS_METRIC_WRAP8 && p->metric != VCS_METRIC_SAD)
+        return fail(ctx, VCS_E_INVALID, "unknown metric %d", p->metric);
+    if (p->hi < p->lo) return fail(ctx, VCS_E_INVALID, "empty offset interval [%d,%d]", p->lo, p->hi);
+    if (p->H > 32767 || p->W > 32767)
+        return fail(ctx, VCS_E_INVALID, "frame larger than int16 motion vectors allow");
+    if ((long long)255 * 3 * p->bs * p->bs >= (1ll << 32))
+        return fail(ctx, VCS_E_INVALID, "block too large for 32-bit costs");
+    return VCS_OK;
+}
+
+MeGeom make_geom(const vcs_me_params *p) {
+    MeGeom g;
+    g.H = p->H; g.W = p->W; g.bs = p->bs; g.lo = p->lo; g.hi = p->hi; g.step = p->step;
+    g.slack = p->slack; g.nbx = p->W / p->bs; g.nby = p->H / p->bs; g.static_thr = p->static_thr;
+    return g;
+}
+
+FrameAddr pair_addr(const uint8_t *cur, const uint8_t *ref) {
+    FrameAddr fa;
+    fa.cur_base = cur; fa.ref_base = ref;
+    fa.cur_gop_stride = 0; fa.cur_frame_stride = 0; fa.ref_gop_stride = 0; fa.ppg = 1;
+    return fa;
+}
+
+// Clip under the reference's GOP rule (encoder.py:25,51-52).  Only whole GOPs plus a trailing
+// partial GOP are addressed: P-ordinal p -> gop p/(g-1), frame 1 + p%(g-1) inside it.
+FrameAddr clip_addr(const uint8_t *frames, int H, int W, int gop_len) {
+    const long long fs = (long long)H * W * 3;
+    FrameAddr fa;
+    fa.cur_base = frames + fs; fa.ref_base = frames;
+    fa.cur_gop_stride = fs * gop_len; fa.cur_frame_stride = fs; fa.ref_gop_stride = fs * gop_len;
+    fa.ppg = gop_len - 1;
+    return fa;
+}
+
+int launch_me(vcs_ctx *ctx, cudaStream_t st, const vcs_me_params *p, const FrameAddr &fa, int npairs,
+              int16_t *mv, uint32_t *cost, uint8_t *flags) {
+    int rc = check_me_params(ctx, p);
+    if (rc) return rc;
+    if (npairs <= 0) return VCS_OK;
+    if (!mv) return fail(ctx, VCS_E_INVALID, "mv output is NULL");
+    const MeGeom g = make_geom(p);
+    const int N = g.nbx * g.nby;
+    if (p->kernel != VCS_ME_GENERIC) {
+        int used = 0;
+        rc = me_tiled_launch(ctx->tiled, st, p->metric, g, fa, npairs, mv, cost, flags, ctx->sm_count,
+                             ctx->smem_optin, &used, ctx->err, sizeof(ctx->err));
+        if (rc) return rc;
+        if (used) { ctx->launches += used; return VCS_OK; }
+        if (p->kernel == VCS_ME_TILED)
+            return fail(ctx, VCS_E_UNSUPPORTED, "tiled ME kernel does not cover bs=%d step=%d lo=%d hi=%d",
+                        p->bs, p->step, p->lo, p->hi);
+    }
+    const int rw = (3 * g.bs + 3) / 4;
+    const size_t smem = (size_t)g.bs * rw * 4;
+    if (smem > 48 * 1024) return fail(ctx, VCS_E_UNSUPPORTED, "bs=%d too large for the generic kernel", g.bs);
+    dim3 grid(N, npairs);
+    if (p->metric == VCS_METRIC_WRAP8)
+        me_generic_kernel<0><<<grid, ME_GENERIC_THREADS, smem, st>>>(fa, g, mv, cost, flags);
+    else
+        me_generic_kernel<1><<<grid, ME_GENERIC_THREADS, smem, st>>>(fa, g, mv, cost, flags);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return VCS_OK;
+}
+
+int launch_dct(vcs_ctx *ctx, cudaStream_t st, DctArgs &a, int nP) {
+    if (a.H <= 0 || a.W <= 0 || a.H % 8 || a.W % 8)
+        return fail(ctx, VCS_E_INVALID,
+                    "H=%d W=%d must be multiples of 8 (the reference resizes, DCTcompressor.py:52)", a.H, a.W);
+    if (a.coef_mode < 0 || a.coef_mode > 2) return fail(ctx, VCS_E_INVALID, "coef_mode %d", a.coef_mode);
+    if (nP <= 0) return VCS_OK;
+    a.Q = ctx->d_Q;
+    dim3 grid((a.W + DCT_TILE_W - 1) / DCT_TILE_W, a.H / 8, nP);
+    dct_stage_kernel<<<grid, DCT_THREADS, DCT_SMEM_BYTES, st>>>(a);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return VCS_OK;
+}
+
+size_t coef_elem(int coef_mode) { return coef_mode == VCS_COEF_I16_RINT ? 2 : 8; }
+
+EvTriple *next_events(vcs_ctx *ctx) {
+    if (!ctx->timing) return nullptr;
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        EvTriple t;
+        if (cudaEventCreate(&t.e0) || cudaEventCreate(&t.e1) || cudaEventCreate(&t.e2)) return nullptr;
+        t.has_me = t.has_dct = false;
+        ctx->ev_pool.push_back(t);
+    }
+    EvTriple *t = &ctx->ev_pool[ctx->ev_used++];
+    t->has_me = t->has_dct = false;
+    return t;
+}
+
+// ME + residual/DCT/recon for nP P-frames addressed by fa, on stream st.
+int encode_dev(vcs_ctx *ctx, cudaStream_t st, const vcs_me_params *p, const FrameAddr &fa, int nP,
+               int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef, uint8_t *recon) {
+    EvTriple *ev = next_events(ctx);
+    if (ev) CK(ctx, cudaEventRecord(ev->e0, st));
+    int rc = launch_me(ctx, st, p, fa, nP, mv, cost, flags);
+    if (rc) return rc;
+    if (ev) { CK(ctx, cudaEventRecord(ev->e1, st)); ev->has_me = true; }
+    if (coef || recon) {
+        DctArgs a;
+        memset(&a, 0, sizeof(a));
+        a.H = p->H; a.W = p->W; a.fa = fa; a.has_fa = 1; a.mv = mv; a.bs = p->bs;
+        a.nbx = p->W / p->bs; a.nby = p->H / p->bs; a.forward = 1; a.inverse = recon != nullptr;
+        a.coef_mode = coef_mode; a.coef = coef; a.recon = recon;
+        rc = launch_dct(ctx, st, a, nP);
+        if (rc) return rc;
+        if (ev) { CK(ctx, cudaEventRecord(ev->e2, st)); ev->has_dct = true; }
+    }
+    return VCS_OK;
+}
+
+}  // namespace
+
+template <int W>
+int run_mb(vcs_ctx *ctx, int iters, double *rate, double *mhz) {
+    const int blocks = ctx->sm_count * 8;
+    uint32_t *d_out; long long *d_cyc; int rc;
+    if ((rc = dev_buf(ctx, S_MB, (size_t)blocks * MB_THREADS * 4, (void **)&d_out))) return rc;
+    if ((rc = dev_buf(ctx, S_CYC, 8, (void **)&d_cyc))) return rc;
+    cudaEvent_t e0, e1;
+    CK(ctx, cudaEventCreate(&e0));
+    CK(ctx, cudaEventCreate(&e1));
+    cudaStream_t st = ctx->stream;
+    microbench_kernel<W><<<blocks, MB_THREADS, 0, st>>>(d_out, iters / 4 + 1, 12345u, d_cyc);  // warm-up
+    CK(ctx, cudaEventRecord(e0, st));
+    microbench_kernel<W><<<blocks, MB_THREADS, 0, st>>>(d_out, iters, 12345u, d_cyc);
+    CK(ctx, cudaEventRecord(e1, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    float ms;
+    CK(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    long long cyc = 0;
+    CK(ctx, cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double warps = (double)blocks * MB_THREADS / 32.0;
+    double ops = warps * (double)iters * mb_ops_per_iter(W);
+    if (W == 5) ops /= 3.0;  // report words/s/32 for the wrap8 triple
+    if (W == 6) ops = warps * (double)iters * MB_ACC * MB_UNROLL;  // count the VABSDIFF4s only
+    if (rate) *rate = ops / (ms * 1e-3);
+    if (mhz) *mhz = (double)cyc / (ms * 1e3);
+    return VCS_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int vcs_version(void) { return 100; }
+
+const char *vcs_last_error(const vcs_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+
+int vcs_dct_matrix(double *C) {
+    // DCTCompressor._dctMatrix (DCTcompressor.py:124-133): host libm, like Python's math module
+    if (!C) return VCS_E_INVALID;
+    const int N = 8;
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j)
+            C[i * N + j] = i == 0 ? 1.0 / sqrt((double)N)
+                                  : sqrt(2.0 / N) * cos((double)((2 * j + 1) * i) * M_PI / (double)(2 * N));
+    return VCS_OK;
+}
+
+int vcs_q_tables(double qf, double *Q) {
+    // DCTcompressor.py:11-38.  Luma entry [1][5] is 48 as in the reference, not Annex K's 58.
+    static const int QY[64] = {16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  48,  60,  55,
+                               14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+                               18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+                               49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+    static const int QC[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99,
+                               24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99,
+                               99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                               99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+    if (!Q) return VCS_E_INVALID;
+    double scale;
+    if (qf < 50 && qf > 1) scale = 50 / qf;
+    else if (qf < 100) scale = (100 - qf) / 50;
+    else return VCS_E_INVALID;
+    for (int k = 0; k < 64; ++k) {
+        double y = nearbyint(QY[k] * scale), c = nearbyint(QC[k] * scale);  // np.round: half-even
+        y = fmin(fmax(y, 1.0), 255.0);
+        c = fmin(fmax(c, 1.0), 255.0);
+        Q[k] = y; Q[64 + k] = c; Q[128 + k] = c;
+    }
+    return VCS_OK;
+}
+
+int vcs_num_blocks(int H, int W, int bs) { return bs > 0 ? (H / bs) * (W / bs) : 0; }
+
+int vcs_num_p_frames(int T, int gop_len) {
+    if (T <= 0 || gop_len <= 0) return 0;
+    return T - (T + gop_len - 1) / gop_len;
+}
+
+int vcs_me_reference_params(int H, int W, int bs, vcs_me_params *out) {
+    if (!out || bs <= 0) return VCS_E_INVALID;
+    memset(out, 0, sizeof(*out));
+    const int R = 2 * bs;  // motion.py:18
+    out->H = H; out->W = W; out->bs = bs;
+    out->lo = -R; out->hi = R - bs - 1; out->slack = 1;  // motion.py:125-140
+    out->step = (int)nearbyint(bs / 3.0);                // Python round(bs/3), motion.py:132
+    if (out->step < 1) return VCS_E_INVALID;             // range() step 0 raises in the reference
+    out->metric = VCS_METRIC_WRAP8;                      // motion.py:146
+    out->static_thr = 2000;                              // motion.py:8
+    out->kernel = VCS_ME_AUTO;
+    return VCS_OK;
+}
+
+int vcs_me_fullsearch_params(int H, int W, int bs, int R, int metric, int64_t static_thr,
+                             vcs_me_params *out) {
+    if (!out || bs <= 0 || R < 0) return VCS_E_INVALID;
+    memset(out, 0, sizeof(*out));
+    out->H = H; out->W = W; out->bs = bs; out->lo = -R; out->hi = R; out->step = 1; out->slack = 0;
+    out->metric = metric; out->static_thr = static_thr; out->kernel = VCS_ME_AUTO;
+    return VCS_OK;
+}
+
+int vcs_create(int device, vcs_ctx **out) {
+    if (!out) return VCS_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return VCS_E_CUDA;  // no CPU fallback
+    vcs_ctx *ctx = new vcs_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return VCS_E_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&ctx->d_Q, sizeof(ctx->h_Q)) != cudaSuccess) {
+        delete ctx;
+        return VCS_E_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    double C[64];
+    vcs_dct_matrix(C);
+    if (cudaMemcpyToSymbol(c_dct, C, sizeof(C)) != cudaSuccess ||
+        cudaFuncSetAttribute(dct_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)DCT_SMEM_BYTES) != cudaSuccess) {
+        delete ctx;
+        return VCS_E_CUDA;
+    }
+    vcs_q_tables(50.0, ctx->h_Q);  // DCTcompressor.py:29 QF = 50
+    if (cudaMemcpy(ctx->d_Q, ctx->h_Q, sizeof(ctx->h_Q), cudaMemcpyHostToDevice) != cudaSuccess) {
+        delete ctx;
+        return VCS_E_CUDA;
+    }
+    *out = ctx;
+    return VCS_OK;
+}
+
+int vcs_destroy(vcs_ctx *ctx) {
+    if (!ctx) return VCS_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int s = 0; s < NUM_DEV_SLOTS; ++s)
+        if (ctx->dev[s]) cudaFree(ctx->dev[s]);
+    if (ctx->d_Q) cudaFree(ctx->d_Q);
+    for (auto &t : ctx->ev_pool) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
+    for (auto &e : ctx->chunk_events) cudaEventDestroy(e);
+    me_tiled_destroy(ctx->tiled);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    delete ctx;
+    return VCS_OK;
+}
+
+int vcs_set_stream(vcs_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return VCS_E_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return VCS_OK;
+}
+
+int vcs_synchronize(vcs_ctx *ctx) {
+    if (!ctx) return VCS_E_INVALID;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return VCS_OK;
+}
+
+int vcs_device_info(vcs_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin) {
+    if (!ctx) return VCS_E_INVALID;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (smem_optin) *smem_optin = ctx->smem_optin;
+    return VCS_OK;
+}
+
+int64_t vcs_launch_count(const vcs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int vcs_set_q(vcs_ctx *ctx, const double *Q) {
+    if (!ctx || !Q) return VCS_E_INVALID;
+    for (int k = 0; k < 192; ++k)
+        if (!(Q[k] != 0.0)) return fail(ctx, VCS_E_INVALID, "Q[%d] is zero or NaN", k);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->h_Q, Q, sizeof(ctx->h_Q));
+    CK(ctx, cudaMemcpy(ctx->d_Q, ctx->h_Q, sizeof(ctx->h_Q), cudaMemcpyHostToDevice));
+    return VCS_OK;
+}
+
+// ---- motion estimation -------------------------------------------------------------------
+int vcs_me_search_dev(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *cur, const uint8_t *ref,
+                      int16_t *mv, uint32_t *cost, uint8_t *flags) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!cur || !ref) return fail(ctx, VCS_E_INVALID, "frame pointer is NULL");
+    return launch_me(ctx, ctx->stream, p, pair_addr(cur, ref), 1, mv, cost, flags);
+}
+
+int vcs_me_search_clip_dev(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T,
+                           int gop_len, int16_t *mv, uint32_t *cost, uint8_t *flags) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!frames || !p || gop_len < 2 || T < 1) return fail(ctx, VCS_E_INVALID, "bad clip arguments");
+    return launch_me(ctx, ctx->stream, p, clip_addr(frames, p->H, p->W, gop_len),
+                     vcs_num_p_frames(T, gop_len), mv, cost, flags);
+}
+
+int vcs_me_search_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *cur, const uint8_t *ref,
+                       int16_t *mv, uint32_t *cost, uint8_t *flags) {
+    if (!ctx) return VCS_E_INVALID;
+    int rc = check_me_params(ctx, p);
+    if (rc) return rc;
+    if (!cur || !ref || !mv) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    const size_t fs = (size_t)p->H * p->W * 3;
+    const int N = vcs_num_blocks(p->H, p->W, p->bs);
+    uint8_t *d_fr; int16_t *d_mv; uint32_t *d_cost; uint8_t *d_fl;
+    if ((rc = dev_buf(ctx, S_FRAMES, 2 * fs, (void **)&d_fr))) return rc;
+    if ((rc = dev_buf(ctx, S_MV, (size_t)N * 4, (void **)&d_mv))) return rc;
+    if ((rc = dev_buf(ctx, S_COST, (size_t)N * 4, (void **)&d_cost))) return rc;
+    if ((rc = dev_buf(ctx, S_FLAGS, (size_t)N, (void **)&d_fl))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(d_fr, ref, fs, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(d_fr + fs, cur, fs, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_me(ctx, st, p, pair_addr(d_fr + fs, d_fr), 1, d_mv, d_cost, d_fl))) return rc;
+    CK(ctx, cudaMemcpyAsync(mv, d_mv, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    if (cost) CK(ctx, cudaMemcpyAsync(cost, d_cost, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+    if (flags) CK(ctx, cudaMemcpyAsync(flags, d_fl, (size_t)N, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return VCS_OK;
+}
+
+// ---- MC / wrap arithmetic ------------------------------------------------------------------
+int vcs_mc_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref, const int16_t *mv, uint8_t *pred) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!ref || !mv || !pred || bs <= 0 || H < bs || W < bs) return fail(ctx, VCS_E_INVALID, "bad MC arguments");
+    const size_t npix = (size_t)H * W;
+    int blocks = (int)((npix + 255) / 256);
+    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+    mc_kernel<<<blocks, 256, 0, ctx->stream>>>(ref, mv, H, W, bs, W / bs, H / bs, pred);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return VCS_OK;
+}
+
+int vcs_mc_host(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref, const int16_t *mv, uint8_t *pred) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!ref || !mv || !pred || bs <= 0 || H < bs || W < bs) return fail(ctx, VCS_E_INVALID, "bad MC arguments");
+    const size_t fs = (size_t)H * W * 3;
+    const int N = vcs_num_blocks(H, W, bs);
+    // the reference would raise IndexError / broadcast errors on an out-of-frame vector
+    for (int k = 0; k < N; ++k) {
+        int x = (k % (W / bs)) * bs + mv[2 * k], y = (k / (W / bs)) * bs + mv[2 * k + 1];
+        if (x < 0 || y < 0 || x + bs > W || y + bs > H)
+            return fail(ctx, VCS_E_INVALID, "motion vector %d points outside the frame", k);
+    }
+    uint8_t *d_fr; int16_t *d_mv; int rc;
+    if ((rc = dev_buf(ctx, S_FRAMES, 2 * fs, (void **)&d_fr))) return rc;
+    if ((rc = dev_buf(ctx, S_MV, (size_t)N * 4, (void **)&d_mv))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(d_fr, ref, fs, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(d_mv, mv, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = vcs_mc_dev(ctx, H, W, bs, d_fr, d_mv, d_fr + fs))) return rc;
+    CK(ctx, cudaMemcpyAsync(pred, d_fr + fs, fs, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return VCS_OK;
+}
+
+static int wrap_dev(vcs_ctx *ctx, int add, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!a || !b || !out) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    if (n == 0) return VCS_OK;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+    if (add) wrap_kernel<1><<<blocks, 256, 0, ctx->stream>>>(a, b, n, out);
+    else wrap_kernel<0><<<blocks, 256, 0, ctx->stream>>>(a, b, n, out);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return VCS_OK;
+}
+
+static int wrap_host(vcs_ctx *ctx, int add, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!a || !b || !out) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    if (n == 0) return VCS_OK;
+    uint8_t *d; int rc;
+    if ((rc = dev_buf(ctx, S_FRAMES, 3 * n, (void **)&d))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(d, a, n, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(d + n, b, n, cudaMemcpyHostToDevice, st));
+    if ((rc = wrap_dev(ctx, add, d, d + n, n, d + 2 * n))) return rc;
+    CK(ctx, cudaMemcpyAsync(out, d + 2 * n, n, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return VCS_OK;
+}
+
+int vcs_sub_wrap_dev(vcs_ctx *c, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *o) { return wrap_dev(c, 0, a, b, n, o); }
+int vcs_add_wrap_dev(vcs_ctx *c, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *o) { return wrap_dev(c, 1, a, b, n, o); }
+int vcs_sub_wrap_host(vcs_ctx *c, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *o) { return wrap_host(c, 0, a, b, n, o); }
+int vcs_add_wrap_host(vcs_ctx *c, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *o) { return wrap_host(c, 1, a, b, n, o); }
+
+// ---- DCT stage -------------------------------------------------------------------------------
+int vcs_compress_dev(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, int coef_mode, void *coef) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!bgr || !coef) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    DctArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H = H; a.W = W; a.img = bgr; a.bs = 8; a.forward = 1; a.coef_mode = coef_mode; a.coef = coef;
+    return launch_dct(ctx, ctx->stream, a, 1);
+}
+
+int vcs_compress_host(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, int coef_mode, void *coef) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!bgr || !coef) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    if (H <= 0 || W <= 0 || H % 8 || W % 8 || coef_mode < 0 || coef_mode > 2)
+        return fail(ctx, VCS_E_INVALID, "H=%d W=%d must be multiples of 8; coef_mode=%d", H, W, coef_mode);
+    const size_t npix = (size_t)H * W;
+    uint8_t *d_img; void *d_coef; int rc;
+    if ((rc = dev_buf(ctx, S_FRAMES, npix * 3, (void **)&d_img))) return rc;
+    if ((rc = dev_buf(ctx, S_COEF, npix * 3 * coef_elem(coef_mode), &d_coef))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(d_img, bgr, npix * 3, cudaMemcpyHostToDevice, st));
+    if ((rc = vcs_compress_dev(ctx, H, W, d_img, coef_mode, d_coef))) return rc;
+    CK(ctx, cudaMemcpyAsync(coef, d_coef, npix * 3 * coef_elem(coef_mode), cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return VCS_OK;
+}
+
+int vcs_decompress_dev(vcs_ctx *ctx, int H, int W, int coef_mode, const void *coef, const uint8_t *pred,
+                       uint8_t *bgr) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!coef || !bgr) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    DctArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H = H; a.W = W; a.bs = 8; a.forward = 0; a.inverse = 1; a.coef_mode = coef_mode;
+    a.coef = const_cast<void *>(coef); a.pred_in = pred; a.recon = bgr;
+    return launch_dct(ctx, ctx->stream, a, 1);
+}
+
+int vcs_decompress_host(vcs_ctx *ctx, int H, int W, int coef_mode, const void *coef, const uint8_t *pred,
+                        uint8_t *bgr) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!coef || !bgr) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    if (H <= 0 || W <= 0 || H % 8 || W % 8 || coef_mode < 0 || coef_mode > 2)
+        return fail(ctx, VCS_E_INVALID, "H=%d W=%d must be multiples of 8; coef_mode=%d", H, W, coef_mode);
+    const size_t npix = (size_t)H * W;
+    uint8_t *d_img; void *d_coef; int rc;
+    if ((rc = dev_buf(ctx, S_FRAMES, npix * 6, (void **)&d_img))) return rc;
+    if ((rc = dev_buf(ctx, S_COEF, npix * 3 * coef_elem(coef_mode), &d_coef))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(d_coef, coef, npix * 3 * coef_elem(coef_mode), cudaMemcpyHostToDevice, st));
+    if (pred) CK(ctx, cudaMemcpyAsync(d_img + npix * 3, pred, npix * 3, cudaMemcpyHostToDevice, st));
+    if ((rc = vcs_decompress_dev(ctx, H, W, coef_mode, d_coef, pred ? d_img + npix * 3 : nullptr, d_img)))
+        return rc;
+    CK(ctx, cudaMemcpyAsync(bgr, d_img, npix * 3, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return VCS_OK;
+}
+
+// ---- fused clip paths ------------------------------------------------------------------------
+int vcs_residual_dct_clip_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *frames, int T, int gop_len,
+                              const int16_t *mv, int coef_mode, void *coef, uint8_t *recon) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!frames || !mv || gop_len < 2 || T < 1 || bs <= 0 || H < bs || W < bs)
+        return fail(ctx, VCS_E_INVALID, "bad clip arguments");
+    DctArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H = H; a.W = W; a.fa = clip_addr(frames, H, W, gop_len); a.has_fa = 1; a.mv = mv; a.bs = bs;
+    a.nbx = W / bs; a.nby = H / bs; a.forward = 1; a.inverse = recon != nullptr;
+    a.coef_mode = coef_mode; a.coef = coef; a.recon = recon;
+    return launch_dct(ctx, ctx->stream, a, vcs_num_p_frames(T, gop_len));
+}
+
+int vcs_encode_clip_dev(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
+                        int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef,
+                        uint8_t *recon) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!frames || !p || gop_len < 2 || T < 1) return fail(ctx, VCS_E_INVALID, "bad clip arguments");
+    return encode_dev(ctx, ctx->stream, p, clip_addr(frames, p->H, p->W, gop_len),
+                      vcs_num_p_frames(T, gop_len), coef_mode, mv, cost, flags, coef, recon);
+}
+
+int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
+                         int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef,
+                         uint8_t *recon) {
+    if (!ctx) return VCS_E_INVALID;
+    int rc = check_me_params(ctx, p);
+    if (rc) return rc;
+    if (!frames || gop_len < 2 || T < 1) return fail(ctx, VCS_E_INVALID, "bad clip arguments");
+    if ((coef || recon) && (p->H % 8 || p->W % 8))
+        return fail(ctx, VCS_E_INVALID, "H=%d W=%d must be multiples of 8 for the DCT stage", p->H, p->W);
+    const size_t fs = (size_t)p->H * p->W * 3, npix = (size_t)p->H * p->W;
+    const int N = vcs_num_blocks(p->H, p->W, p->bs);
+    const int nP = vcs_num_p_frames(T, gop_len);
+    const size_t ce = coef_elem(coef_mode);
+    uint8_t *d_fr; int16_t *d_mv; uint32_t *d_cost; uint8_t *d_fl; void *d_coef = nullptr; uint8_t *d_rec = nullptr;
+    if ((rc = dev_buf(ctx, S_FRAMES, fs * T, (void **)&d_fr))) return rc;
+    if ((rc = dev_buf(ctx, S_MV, (size_t)nP * N * 4 + 4, (void **)&d_mv))) return rc;
+    if ((rc = dev_buf(ctx, S_COST, (size_t)nP * N * 4 + 4, (void **)&d_cost))) return rc;
+    if ((rc = dev_buf(ctx, S_FLAGS, (size_t)nP * N + 4, (void **)&d_fl))) return rc;
+    if (coef && (rc = dev_buf(ctx, S_COEF, (size_t)nP * npix * 3 * ce + 8, &d_coef))) return rc;
+    if (recon && (rc = dev_buf(ctx, S_RECON, (size_t)nP * fs + 4, (void **)&d_rec))) return rc;
+
+    // Pipeline GOP-chunk by GOP-chunk: copy-in on s_h2d, kernels on the compute stream, copy-out
+    // on s_d2h; PCIe is full duplex so the three overlap.
+    const int nG = (T + gop_len - 1) / gop_len;
+    int chunk_g = nG >= 8 ? (nG + 7) / 8 : 1;
+    const int nchunks = (nG + chunk_g - 1) / chunk_g;
+    while ((int)ctx->chunk_events.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->chunk_events.push_back(e);
+    }
+    cudaStream_t sc = ctx->stream;
+    for (int c = 0; c < nchunks; ++c) {
+        const int g0 = c * chunk_g, g1 = (g0 + chunk_g < nG) ? g0 + chunk_g : nG;
+        const int t0 = g0 * gop_len, t1 = (g1 * gop_len < T) ? g1 * gop_len : T;
+        const int p0 = vcs_num_p_frames(t0, gop_len), p1 = vcs_num_p_frames(t1, gop_len);
+        CK(ctx, cudaMemcpyAsync(d_fr + fs * t0, frames + fs * t0, fs * (t1 - t0), cudaMemcpyHostToDevice,
+                                ctx->s_h2d));
+        CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c], ctx->s_h2d));
+        CK(ctx, cudaStreamWaitEvent(sc, ctx->chunk_events[2 * c], 0));
+        const int np = p1 - p0;
+        if (np > 0) {
+            FrameAddr fa = clip_addr(d_fr + fs * t0, p->H, p->W, gop_len);
+            rc = encode_dev(ctx, sc, p, fa, np, coef_mode, d_mv + (size_t)p0 * N * 2, d_cost + (size_t)p0 * N,
+                            d_fl + (size_t)p0 * N,
+                            d_coef ? (void *)((char *)d_coef + (size_t)p0 * npix * 3 * ce) : nullptr,
+                            d_rec ? d_rec + (size_t)p0 * fs : nullptr);
+            if (rc) return rc;
+        }
+        CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sc));
+        CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->chunk_events[2 * c + 1], 0));
+        if (np > 0) {
+            if (mv) CK(ctx, cudaMemcpyAsync(mv + (size_t)p0 * N * 2, d_mv + (size_t)p0 * N * 2, (size_t)np * N * 4,
+                                            cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (cost) CK(ctx, cudaMemcpyAsync(cost + (size_t)p0 * N, d_cost + (size_t)p0 * N, (size_t)np * N * 4,
+                                              cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (flags) CK(ctx, cudaMemcpyAsync(flags + (size_t)p0 * N, d_fl + (size_t)p0 * N, (size_t)np * N,
+                                               cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (coef) CK(ctx, cudaMemcpyAsync((char *)coef + (size_t)p0 * npix * 3 * ce,
+                                              (char *)d_coef + (size_t)p0 * npix * 3 * ce,
+                                              (size_t)np * npix * 3 * ce, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (recon) CK(ctx, cudaMemcpyAsync(recon + (size_t)p0 * fs, d_rec + (size_t)p0 * fs, (size_t)np * fs,
+                                               cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
+    CK(ctx, cudaStreamSynchronize(sc));
+    return VCS_OK;
+}
+
+// ---- measurement support ---------------------------------------------------------------------
+int vcs_enable_kernel_timing(vcs_ctx *ctx, int on) {
+    if (!ctx) return VCS_E_INVALID;
+    ctx->timing = on != 0;
+    ctx->ev_used = 0;
+    return VCS_OK;
+}
+
+int vcs_kernel_times(vcs_ctx *ctx, double *me_ms_total, double *dct_ms_total, int *ncalls) {
+    if (!ctx) return VCS_E_INVALID;
+    CK(ctx, cudaDeviceSynchronize());
+    double me = 0, dct = 0;
+    for (size_t k = 0; k < ctx->ev_used; ++k) {
+        EvTriple &t = ctx->ev_pool[k];
+        float ms;
+        if (t.has_me) { CK(ctx, cudaEventElapsedTime(&ms, t.e0, t.e1)); me += ms; }
+        if (t.has_dct) { CK(ctx, cudaEventElapsedTime(&ms, t.e1, t.e2)); dct += ms; }
+    }
+    if (me_ms_total) *me_ms_total = me;
+    if (dct_ms_total) *dct_ms_total = dct;
+    if (ncalls) *ncalls = (int)ctx->ev_used;
+    ctx->ev_used = 0;
+    return VCS_OK;
+}
+
+int vcs_microbench(vcs_ctx *ctx, int which, int iters, double *warp_instr_per_s, double *sm_mhz) {
+    if (!ctx) return VCS_E_INVALID;
+    if (iters <= 0) iters = 2000;
+    switch (which) {
+        case 0: return run_mb<0>(ctx, iters, warp_instr_per_s, sm_mhz);
+        case 1: return run_mb<1>(ctx, iters, warp_instr_per_s, sm_mhz);
+        case 2: return run_mb<2>(ctx, iters, warp_instr_per_s, sm_mhz);
+        case 3: return run_mb<3>(ctx, iters, warp_instr_per_s, sm_mhz);
+        case 4: return run_mb<4>(ctx, iters, warp_instr_per_s, sm_mhz);
+        case 5: return run_mb<5>(ctx, iters, warp_instr_per_s, sm_mhz);
+        case 6: return run_mb<6>(ctx, iters, warp_instr_per_s, sm_mhz);
+        default: return fail(ctx, VCS_E_INVALID, "unknown microbenchmark %d", which);
+    }
+}
+
+}  // extern "C"

@@ -79,8 +79,10 @@ int vcs_version(void);
 int vcs_create(int device, vcs_ctx **out);
 int vcs_destroy(vcs_ctx *ctx);
 const char *vcs_last_error(const vcs_ctx *ctx);
-/* kernels are enqueued on this cudaStream_t (NULL = the context's own stream) */
+/* kernels are enqueued on this cudaStream_t (0 = CUDA's legacy default stream); a new context
+ * starts on a non-blocking stream of its own, vcs_use_own_stream goes back to it */
 int vcs_set_stream(vcs_ctx *ctx, void *cuda_stream);
+int vcs_use_own_stream(vcs_ctx *ctx);
 int vcs_synchronize(vcs_ctx *ctx);
 int vcs_device_info(vcs_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
                     size_t *smem_per_block_optin);

@@ -49,6 +49,7 @@ SIGNATURES = {
     "vcs_destroy": (_i, [_vp]),
     "vcs_last_error": (C.c_char_p, [_vp]),
     "vcs_set_stream": (_i, [_vp, _vp]),
+    "vcs_use_own_stream": (_i, [_vp]),
     "vcs_synchronize": (_i, [_vp]),
     "vcs_device_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz)]),
     "vcs_launch_count": (C.c_int64, [_vp]),
@@ -88,9 +89,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
-        _build.build()
+    from . import build as _build
+    if not os.path.exists(LIB_PATH) or (_build.stale() and os.path.exists(_build.NVCC)):
+        _build.build()                   # in-tree, next to this file; raises if nvcc fails
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError = header/library mismatch: be loud
@@ -151,6 +152,9 @@ class Context:
     # -- plumbing -------------------------------------------------------------------------
     def set_stream(self, stream_ptr):
         self.call("vcs_set_stream", stream_ptr)
+
+    def use_own_stream(self):
+        self.call("vcs_use_own_stream")
 
     def synchronize(self):
         self.call("vcs_synchronize")

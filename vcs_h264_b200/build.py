@@ -22,9 +22,12 @@ def sources():
     return [os.path.join(d, f) for f in os.listdir(d)] + [os.path.join(HERE, "..", "include", "vcs_b200.h")]
 
 
+def stale():
+    return not os.path.exists(OUT) or any(os.path.getmtime(OUT) < os.path.getmtime(s) for s in sources())
+
+
 def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and all(
-            os.path.getmtime(OUT) >= os.path.getmtime(s) for s in sources()):
+    if not force and not stale():
         return OUT
     cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
     r = subprocess.run(cmd, capture_output=True, text=True)

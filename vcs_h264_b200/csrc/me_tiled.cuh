@@ -1,14 +1,488 @@
-// me_tiled.cuh -- tiled step-1 full-search kernel (placeholder: not built yet, AUTO falls back
-// to me_generic).
+// me_tiled.cuh -- step-1 full-search block matching, the hot kernel of the path (sm_100a).
+//
+// Replaces the candidate loop of MotionProcessor._find_match
+// (InterframeCompression/motion.py:117-152) for step-1 searches (BASELINE.json configs 2/3/5):
+// same candidate set (interval form of include/vcs_b200.h), same cost, same scan-order
+// tie-break, same static early-out (motion.py:109-116).
+//
+// Design (INT32-ALU bound; DESIGN.md "me_tiled"):
+//   * persistent CTAs, one per SM; a work unit is (tile of MX x MY macroblocks, ND x ND chunk of
+//     the offset range).  The reference window of a unit is fetched by ONE TMA tile load
+//     (cp.async.bulk.tensor, zero fill outside the frame) into a double-buffered raw stage while
+//     the previous unit is being searched; the tile's macroblocks come by a second TMA load.
+//   * frames are BGR-interleaved, so a dx shift is 3 bytes and 3 of 4 candidates are not word
+//     aligned.  The raw window is re-laid once per unit into 4 byte-phase copies, transposed to
+//     [phase][word column][row]; after that every candidate reads ALIGNED 128-bit words and every
+//     VABSDIFF4 lane does algorithmic work (no pad byte, no per-use funnel shift).
+//   * thread = (macroblock, dx).  It keeps ND accumulators (all dy of the chunk) and, per word
+//     column, the BS macroblock words in registers; one LDS.128 delivers 4 window rows that feed
+//     up to 4*min(ND,BS) VABSDIFF4.U8.ACC -- ~33 ALU ops per shared-memory load at ND=33.
+//     Row padding RP = 16 (mod 32) words and phase stride PS = 4 (mod 32) words make the 16-byte
+//     bank group of a lane equal (3*dx + const) mod 8, so 8 consecutive dx never conflict.
+//   * the minimum is a packed 64-bit key (cost << 32 | dy_index << 16 | dx_index): min over keys
+//     is the first strict minimum in rows-outer/cols-inner scan order; threads reduce over their
+//     ND dy values in registers and across the macroblock with a shared-memory atomicMin.
+//   * wrap8 cost (the reference's metric): per word t = (r|H) - (c&~H); z = t ^ (~r&H) ^ (c&H);
+//     acc += bytesum(z)  (IADD + LOP3 + IDP.4A instead of one VABSDIFF4).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace vcs {
-struct MeTiledState {};
-inline int me_tiled_launch(MeTiledState &, cudaStream_t, int, const MeGeom &, const FrameAddr &, int,
-                           int16_t *, uint32_t *, uint8_t *, int, size_t, int *used, char *, size_t) {
-    *used = 0;
+
+// ---- compile-time configuration of one kernel variant -------------------------------------
+template <int BS_, int ND_>
+struct TiledCfg {
+    static constexpr int BS = BS_;            // macroblock size (8 or 16)
+    static constexpr int ND = ND_;            // offsets per chunk and axis (9, 17 or 33)
+    static constexpr int MX = ND_ == 9 ? 7 : 5;   // macroblocks per tile, x
+    static constexpr int MY = ND_ == 9 ? 4 : 3;   // macroblocks per tile, y
+    static constexpr int NMB = MX * MY;
+    static constexpr int ITEMS = NMB * ND;    // (macroblock, dx) pairs
+    static constexpr int THREADS = (ITEMS + 127) / 128 * 128;
+    static constexpr int WPR = 3 * BS / 4;    // words per macroblock row
+    static constexpr int WPX = ND - 1 + BS * MX;  // window width, pixels
+    static constexpr int WR = ND - 1 + BS * MY;   // window rows
+    static constexpr int RP = (WR - 16 + 31) / 32 * 32 + 16;  // padded rows, = 16 (mod 32)
+    // raw stage: words per row; multiple of 4 with RAWW/4 odd (conflict-free LDS.128 by row)
+    static constexpr int RAW_NEED = (3 + 3 * WPX + 3 + 3) / 4 + 1;
+    static constexpr int RAWW4 = (RAW_NEED + 3) / 4;
+    static constexpr int RAWW = (RAWW4 % 2 ? RAWW4 : RAWW4 + 1) * 4;
+    static constexpr int NC = ((3 + 3 * (BS * (MX - 1) + ND - 1)) >> 2) + WPR;  // word columns of T
+    static constexpr int PS = (NC * RP + 31) / 32 * 32 + 4;  // phase stride, = 4 (mod 32)
+    static constexpr int CURW = (MX * WPR + 3) / 4 * 4;  // words per row of the raw macroblock tile (TMA: 16 B multiple)
+    static constexpr int CURR = MY * BS;      // rows of it
+    // shared memory carve-up (bytes)
+    static constexpr size_t OFF_T = 0;
+    static constexpr size_t SZ_T = (size_t)4 * PS * 4;
+    static constexpr size_t OFF_RAW = (OFF_T + SZ_T + 127) / 128 * 128;
+    static constexpr size_t SZ_RAW = (size_t)(RAWW * WR + 4) * 4;     // +4: funnel read past the end
+    static constexpr size_t SZ_RAW_AL = (SZ_RAW + 127) / 128 * 128;
+    static constexpr size_t OFF_CRAW = OFF_RAW + 2 * SZ_RAW_AL;
+    static constexpr size_t SZ_CRAW = (size_t)CURW * CURR * 4;
+    static constexpr size_t SZ_CRAW_AL = (SZ_CRAW + 127) / 128 * 128;
+    static constexpr size_t OFF_CURT = OFF_CRAW + 2 * SZ_CRAW_AL;
+    static constexpr size_t SZ_CURT = (size_t)NMB * WPR * BS * 4;      // [mb][w][v]
+    static constexpr size_t OFF_MISC = (OFF_CURT + 2 * SZ_CURT + 127) / 128 * 128;  // 2: wrap8 L/H
+    static constexpr size_t SZ_MISC = 8 * NMB + 8 * NMB + 4 * NMB + 4 * NMB + 64;
+    static constexpr size_t SMEM = OFF_MISC + SZ_MISC + 128;
+};
+
+struct TiledArgs {
+    int H, W, nbx, nby;
+    int lo, hi, slack;
+    long long static_thr;
+    int tiles_x, tiles_y;      // tiles per frame
+    int ncy, ncx;              // chunks of the offset range per axis
+    int zchunk;                // index (cy*ncx+cx) of the chunk holding offset (0,0), or 0
+    int npairs, ppg;
+    int16_t *mv;
+    uint32_t *cost;
+    uint8_t *flags;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ uint4 lds128(const uint32_t *p) { return *reinterpret_cast<const uint4 *>(p); }
+
+__device__ __forceinline__ int floordiv4(int v) { return v >> 2; }  // arithmetic shift = floor for negatives
+
+// ---- the kernel ---------------------------------------------------------------------------------
+template <class C, int METRIC>
+__global__ void __launch_bounds__(C::THREADS, 1)
+me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_cur,
+                const TiledArgs a) {
+    constexpr int BS = C::BS, ND = C::ND, MX = C::MX, NMB = C::NMB, WPR = C::WPR, RP = C::RP, PS = C::PS;
+    constexpr uint32_t Hm = 0x80808080u;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint32_t *sT = reinterpret_cast<uint32_t *>(smem + C::OFF_T);
+    uint32_t *sCurT = reinterpret_cast<uint32_t *>(smem + C::OFF_CURT);           // SAD: c ; wrap8: c & ~H
+    uint32_t *sCurH = sCurT + NMB * WPR * BS;                                      // wrap8: c & H
+    unsigned long long *sBest = reinterpret_cast<unsigned long long *>(smem + C::OFF_MISC);
+    unsigned long long *sDyMask = sBest + NMB;                                     // valid dy bits per mb
+    uint32_t *sStatic = reinterpret_cast<uint32_t *>(sDyMask + NMB);               // 0 / 1 per mb
+    uint32_t *sStaticS = sStatic + NMB;                                            // static sum S
+    uint64_t *sBar = reinterpret_cast<uint64_t *>(sStaticS + NMB);                 // 2 mbarriers (8B aligned)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nch = a.ncy * a.ncx;
+    const int tiles_per_pair = a.tiles_x * a.tiles_y;
+    const long long ntiles = (long long)tiles_per_pair * a.npairs;
+    // tiles of this CTA: blockIdx.x, +gridDim.x, ...
+    const long long my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_units = my_tiles * nch;
+    if (n_units == 0) return;
+
+    // geometry of work unit s of this CTA
+    auto unit_geom = [&](long long s, int &p, int &tx, int &ty, int &cy, int &cx, bool &first, bool &last) {
+        const long long tile = blockIdx.x + (s / nch) * gridDim.x;
+        const int c = (int)(s % nch);
+        const int cc = (c + a.zchunk) % nch;          // the chunk holding offset (0,0) goes first
+        first = c == 0;
+        last = c == nch - 1;
+        p = (int)(tile / tiles_per_pair);
+        const int t = (int)(tile - (long long)p * tiles_per_pair);
+        ty = t / a.tiles_x;
+        tx = t - ty * a.tiles_x;
+        cy = cc / a.ncx;
+        cx = cc - cy * a.ncx;
+    };
+    auto issue = [&](long long s) {   // one elected thread: arm the barrier, start both TMA loads
+        int p, tx, ty, cy, cx; bool f, l;
+        unit_geom(s, p, tx, ty, cy, cx, f, l);
+        const int b = (int)(s & 1);
+        const int xw0 = tx * MX * BS + a.lo + cx * ND, yw0 = ty * C::MY * BS + a.lo + cy * ND;
+        mbar_expect_tx(&sBar[b], (uint32_t)(C::RAWW * C::WR * 4 + C::CURW * C::CURR * 4));
+        tma_load_3d(smem + C::OFF_RAW + b * C::SZ_RAW_AL, &tm_ref, &sBar[b], floordiv4(3 * xw0), yw0,
+                    p / a.ppg);
+        tma_load_4d(smem + C::OFF_CRAW + b * C::SZ_CRAW_AL, &tm_cur, &sBar[b], tx * MX * WPR, ty * C::MY * BS,
+                    p % a.ppg, p / a.ppg);
+    };
+
+    if (tid == 0) {
+        mbar_init(&sBar[0], 1);
+        mbar_init(&sBar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        issue(0);
+        if (n_units > 1) issue(1);
+    }
+
+    // per-thread role in the search: (macroblock, dx index inside the chunk)
+    const int mb = tid / ND, dxw = tid - mb * ND;
+    const int mbx = mb % MX, mby = mb / MX;
+    const bool has_item = tid < C::ITEMS;
+
+    for (long long s = 0; s < n_units; ++s) {
+        int p, tx, ty, cy, cx; bool first, last;
+        unit_geom(s, p, tx, ty, cy, cx, first, last);
+        const int b = (int)(s & 1);
+        const int xw0 = tx * MX * BS + a.lo + cx * ND, yw0 = ty * C::MY * BS + a.lo + cy * ND;
+        const int ao = 3 * xw0 - 4 * floordiv4(3 * xw0);   // byte offset of the window inside raw word 0
+        mbar_wait(&sBar[b], (uint32_t)((s >> 1) & 1));
+
+        // ---- re-lay the raw window: 4 byte phases, transposed [phase][word col][row] ----------
+        {
+            const uint32_t *raw = reinterpret_cast<const uint32_t *>(smem + C::OFF_RAW + b * C::SZ_RAW_AL);
+            constexpr int RG = (C::WR + 31) / 32, JQ = (C::NC + 3) / 4;   // row groups x column quads
+            for (int task = warp; task < RG * JQ; task += C::THREADS / 32) {
+                const int rg = task / JQ, jq = task - rg * JQ;
+                const int r = rg * 32 + lane;
+                if (r < C::WR) {
+                    const uint32_t *src = raw + r * C::RAWW + 4 * jq;
+                    const uint4 q = lds128(src);
+                    const uint32_t nx = src[4];
+                    const uint32_t wv[5] = {q.x, q.y, q.z, q.w, nx};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = 4 * jq + e;
+                        if (j < C::NC) {
+                            uint32_t *dst = sT + j * RP + r;
+                            dst[0] = wv[e];
+                            dst[PS] = __funnelshift_r(wv[e], wv[e + 1], 8);
+                            dst[2 * PS] = __funnelshift_r(wv[e], wv[e + 1], 16);
+                            dst[3 * PS] = __funnelshift_r(wv[e], wv[e + 1], 24);
+                        }
+                    }
+                }
+            }
+            // macroblocks: raw [row][word] -> [mb][w][v]
+            const uint32_t *craw = reinterpret_cast<const uint32_t *>(smem + C::OFF_CRAW + b * C::SZ_CRAW_AL);
+            for (int k = tid; k < NMB * WPR * BS; k += C::THREADS) {
+                const int v = k % BS, w = (k / BS) % WPR, m = k / (BS * WPR);
+                const uint32_t c = craw[((m / MX) * BS + v) * C::CURW + (m % MX) * WPR + w];
+                if (METRIC == 0) { sCurT[k] = c & ~Hm; sCurH[k] = c & Hm; }
+                else sCurT[k] = c;
+            }
+            if (tid < NMB) {
+                if (first) { sBest[tid] = ~0ull; sStatic[tid] = 0; }
+                // valid dy of this chunk for macroblock row (tid / MX): inside [lo,hi] and inside the frame
+                const int y = (ty * C::MY + tid / MX) * BS;
+                unsigned long long m = 0;
+                for (int d = 0; d < ND; ++d) {
+                    const int off = a.lo + cy * ND + d, i = y + off;
+                    if (off <= a.hi && i >= 0 && i <= a.H - BS - a.slack) m |= 1ull << d;
+                }
+                sDyMask[tid] = m;
+            }
+        }
+        __syncthreads();   // T, curT ready; raw stage b is free again
+        if (tid == 0 && s + 2 < n_units) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(s + 2);
+        }
+
+        // ---- static test (motion.py:109-116), on the chunk that holds offset (0,0) ------------
+        if (first && a.static_thr >= 0) {
+            const int d0 = -(a.lo + cy * ND), x0w = -(a.lo + cx * ND);   // window-relative position of (0,0)
+            for (int m = warp; m < NMB; m += C::THREADS / 32) {
+                const int sb = ao + 3 * (BS * (m % MX) + x0w);
+                const uint32_t *col = sT + (sb & 3) * PS + (sb >> 2) * RP + BS * (m / MX) + d0;
+                uint32_t sad = 0, sr = 0, sc = 0;
+                for (int k = lane; k < WPR * BS; k += 32) {
+                    const int w = k / BS, v = k - w * BS;
+                    const uint32_t r = col[w * RP + v];
+                    uint32_t c = sCurT[(m * WPR + w) * BS + v];
+                    if (METRIC == 0) c |= sCurH[(m * WPR + w) * BS + v];
+                    sad = sad4_acc(r, c, sad);
+                    sr = bytesum_acc(r, sr);
+                    sc = bytesum_acc(c, sc);
+                }
+                int part = (int)sad + (int)sr - (int)sc;   // 2 * sum max(ref - cur, 0)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                if (lane == 0) {
+                    const long long S = part / 2;
+                    sStatic[m] = S <= a.static_thr;
+                    sStaticS[m] = (uint32_t)S;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- the search ---------------------------------------------------------------------------
+        const int gx = tx * MX + mbx, gy = ty * C::MY + mby;     // macroblock coordinates in the frame
+        bool active = has_item && gx < a.nbx && gy < a.nby && !sStatic[has_item ? mb : 0];
+        if (active) {
+            const int offx = a.lo + cx * ND + dxw, j = gx * BS + offx;
+            active = offx <= a.hi && j >= 0 && j <= a.W - BS - a.slack;
+        }
+        const unsigned long long dymask = has_item ? sDyMask[mb] : 0;
+        if (active && dymask) {
+            const int sb = ao + 3 * (BS * mbx + dxw);
+            const uint32_t *col = sT + (sb & 3) * PS + (sb >> 2) * RP + BS * mby;
+            const uint32_t *cl = sCurT + mb * WPR * BS;
+            const uint32_t *ch = sCurH + mb * WPR * BS;
+            uint32_t acc[ND];
+#pragma unroll
+            for (int d = 0; d < ND; ++d) acc[d] = 0;
+#pragma unroll 1
+            for (int w = 0; w < WPR; ++w) {
+                uint32_t c[BS], chh[METRIC == 0 ? BS : 1];
+#pragma unroll
+                for (int q = 0; q < BS / 4; ++q) {
+                    const uint4 t = lds128(cl + w * BS + 4 * q);
+                    c[4 * q] = t.x; c[4 * q + 1] = t.y; c[4 * q + 2] = t.z; c[4 * q + 3] = t.w;
+                    if (METRIC == 0) {
+                        const uint4 u = lds128(ch + w * BS + 4 * q);
+                        chh[4 * q] = u.x; chh[4 * q + 1] = u.y; chh[4 * q + 2] = u.z; chh[4 * q + 3] = u.w;
+                    }
+                }
+                const uint32_t *cw = col + w * RP;
+                constexpr int ROWS = ND + BS - 1;
+#pragma unroll
+                for (int rq = 0; rq < (ROWS + 3) / 4; ++rq) {
+                    const uint4 t = lds128(cw + 4 * rq);
+                    const uint32_t rr[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int r = 4 * rq + e;        // window row relative to the macroblock row
+                        if (r < ROWS) {
+                            if (METRIC == 0) {
+                                const uint32_t r1 = rr[e] | Hm, r2 = ~rr[e] & Hm;
+#pragma unroll
+                                for (int d = 0; d < ND; ++d) {
+                                    const int v = r - d;
+                                    if (v >= 0 && v < BS) {
+                                        const uint32_t z = (r1 - c[v]) ^ r2 ^ chh[v];
+                                        acc[d] = __dp4a(z, 0x01010101u, acc[d]);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int d = 0; d < ND; ++d) {
+                                    const int v = r - d;
+                                    if (v >= 0 && v < BS) acc[d] = sad4_acc(rr[e], c[v], acc[d]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // first strict minimum in scan order: key = cost | global dy index | global dx index
+            unsigned long long best = ~0ull;
+            const unsigned long long xkey = (unsigned long long)(cx * ND + dxw);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const unsigned long long key =
+                    ((unsigned long long)acc[d] << 32) | ((unsigned long long)(cy * ND + d) << 16) | xkey;
+                if (((dymask >> d) & 1) && key < best) best = key;
+            }
+            atomicMin(&sBest[mb], best);
+        }
+        __syncthreads();   // search of this unit done: T may be overwritten, sBest is complete
+
+        if (last && tid < NMB) {
+            const int ox = tx * MX + tid % MX, oy = ty * C::MY + tid / MX;
+            if (ox < a.nbx && oy < a.nby) {
+                const size_t o = (size_t)p * a.nbx * a.nby + (size_t)oy * a.nbx + ox;
+                const unsigned long long k = sBest[tid];
+                int mvx, mvy; uint32_t cst; uint8_t fl;
+                if (sStatic[tid]) { mvx = 0; mvy = 0; cst = sStaticS[tid]; fl = 1; }
+                else if (k == ~0ull) { mvx = -ox * BS; mvy = -oy * BS; cst = 0xFFFFFFFFu; fl = 2; }
+                else {
+                    mvx = a.lo + (int)(k & 0xffff); mvy = a.lo + (int)((k >> 16) & 0xffff);
+                    cst = (uint32_t)(k >> 32); fl = 0;
+                }
+                a.mv[2 * o] = (int16_t)mvx;
+                a.mv[2 * o + 1] = (int16_t)mvy;
+                if (a.cost) a.cost[o] = cst;
+                if (a.flags) a.flags[o] = fl;
+            }
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+struct MeTiledState {
+    PFN_encodeTiled encode = nullptr;
+    bool attr_set[2][3][2] = {{{false}}};
+    int occupancy[2][3][2] = {{{0}}};
+};
+
+inline void me_tiled_destroy(MeTiledState &) {}
+
+template <class C, int METRIC>
+int me_tiled_run(MeTiledState &st, cudaStream_t stream, const MeGeom &g, const FrameAddr &fa, int npairs,
+                 int16_t *mv, uint32_t *cost, uint8_t *flags, int sm_count, size_t smem_optin, int bi, int ni,
+                 char *err, size_t errlen) {
+    if (C::SMEM > smem_optin) { snprintf(err, errlen, "tiled ME needs %zu B shared memory", C::SMEM); return -4; }
+    auto kern = me_tiled_kernel<C, METRIC>;
+    if (!st.attr_set[bi][ni][METRIC]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::THREADS, C::SMEM);
+        if (e != cudaSuccess || occ < 1) { snprintf(err, errlen, "tiled ME kernel does not fit an SM"); return -2; }
+        st.occupancy[bi][ni][METRIC] = occ;
+        st.attr_set[bi][ni][METRIC] = true;
+    }
+    const int pitch = 3 * g.W;
+    const long long fs = (long long)pitch * g.H;
+    const int nG = (npairs + fa.ppg - 1) / fa.ppg;
+    // reference frames: words x rows x gop
+    CUtensorMap tm_ref, tm_cur;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)pitch / 4, (cuuint64_t)g.H, (cuuint64_t)nG};
+        cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)(fa.ref_gop_stride ? fa.ref_gop_stride : fs)};
+        cuuint32_t box[3] = {(cuuint32_t)C::RAWW, (cuuint32_t)C::WR, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = st.encode(&tm_ref, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)fa.ref_base, dims, strides, box,
+                               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(ref) -> %d", (int)r); return -2; }
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)pitch / 4, (cuuint64_t)g.H, (cuuint64_t)fa.ppg, (cuuint64_t)nG};
+        cuuint64_t strides[3] = {(cuuint64_t)pitch, (cuuint64_t)(fa.cur_frame_stride ? fa.cur_frame_stride : fs),
+                                 (cuuint64_t)(fa.cur_gop_stride ? fa.cur_gop_stride : fs * fa.ppg)};
+        cuuint32_t box[4] = {(cuuint32_t)C::CURW, (cuuint32_t)C::CURR, 1, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = st.encode(&tm_cur, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void *)fa.cur_base, dims, strides, box,
+                               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled(cur) -> %d", (int)r); return -2; }
+    }
+    TiledArgs a;
+    a.H = g.H; a.W = g.W; a.nbx = g.nbx; a.nby = g.nby; a.lo = g.lo; a.hi = g.hi; a.slack = g.slack;
+    a.static_thr = g.static_thr;
+    a.tiles_x = (g.nbx + C::MX - 1) / C::MX; a.tiles_y = (g.nby + C::MY - 1) / C::MY;
+    const int nd_total = g.hi - g.lo + 1;
+    a.ncy = a.ncx = (nd_total + C::ND - 1) / C::ND;
+    a.zchunk = 0;
+    if (g.lo <= 0 && g.hi >= 0) { const int cz = (-g.lo) / C::ND; a.zchunk = cz * a.ncx + cz; }
+    a.npairs = npairs; a.ppg = fa.ppg; a.mv = mv; a.cost = cost; a.flags = flags;
+    const long long ntiles = (long long)a.tiles_x * a.tiles_y * npairs;
+    long long grid = (long long)sm_count * st.occupancy[bi][ni][METRIC];
+    if (grid > ntiles) grid = ntiles;
+    kern<<<(unsigned)grid, C::THREADS, C::SMEM, stream>>>(tm_ref, tm_cur, a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(err, errlen, "me_tiled launch: %s", cudaGetErrorString(e)); return -2; }
     return 0;
 }
-inline void me_tiled_destroy(MeTiledState &) {}
+
+// Runs the tiled kernel when it covers the request (*used = launches made), else leaves *used = 0.
+inline int me_tiled_launch(MeTiledState &st, cudaStream_t stream, int metric, const MeGeom &g, const FrameAddr &fa,
+                           int npairs, int16_t *mv, uint32_t *cost, uint8_t *flags, int sm_count,
+                           size_t smem_optin, int *used, char *err, size_t errlen) {
+    *used = 0;
+    if (g.step != 1 || (g.bs != 8 && g.bs != 16)) return 0;
+    if (g.W % 16) return 0;                                   // TMA: row pitch must be a multiple of 16 B
+    const long long fs = 3ll * g.W * g.H;
+    if (((uintptr_t)fa.ref_base | (uintptr_t)fa.cur_base) & 15) return 0;
+    if ((fa.ref_gop_stride | fa.cur_gop_stride | fa.cur_frame_stride | fs) & 15) return 0;
+    const int nd_total = g.hi - g.lo + 1;
+    if (nd_total > 0xffff) return 0;
+    if (g.static_thr >= 0 && !(g.lo <= 0 && g.hi >= 0)) return 0;   // static test reads offset (0,0) from the window
+    if (!st.encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+            snprintf(err, errlen, "cuTensorMapEncodeTiled not available from the driver");
+            return -2;
+        }
+        st.encode = (PFN_encodeTiled)fn;
+    }
+    const int ni = nd_total <= 9 ? 0 : (nd_total <= 17 ? 1 : 2);
+    const int bi = g.bs == 16 ? 1 : 0;
+    int rc;
+#define VCS_RUN(BSV, NDV)                                                                                       \
+    rc = metric == 0 ? me_tiled_run<TiledCfg<BSV, NDV>, 0>(st, stream, g, fa, npairs, mv, cost, flags, sm_count, \
+                                                            smem_optin, bi, ni, err, errlen)                    \
+                     : me_tiled_run<TiledCfg<BSV, NDV>, 1>(st, stream, g, fa, npairs, mv, cost, flags, sm_count, \
+                                                            smem_optin, bi, ni, err, errlen)
+    if (bi == 1) {
+        if (ni == 0) { VCS_RUN(16, 9); } else if (ni == 1) { VCS_RUN(16, 17); } else { VCS_RUN(16, 33); }
+    } else {
+        if (ni == 0) { VCS_RUN(8, 9); } else if (ni == 1) { VCS_RUN(8, 17); } else { VCS_RUN(8, 33); }
+    }
+#undef VCS_RUN
+    if (rc) return rc;
+    *used = 1;
+    return 0;
+}
+
 }  // namespace vcs

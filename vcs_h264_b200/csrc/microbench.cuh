@@ -27,7 +27,8 @@ microbench_kernel(uint32_t *out, int iters, uint32_t seed, long long *cycles) {
     s_buf[threadIdx.x] = a;
     s_buf[threadIdx.x + MB_THREADS] = b;
     __syncthreads();
-    const long long t0 = clock64();
+    long long t0, t1;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0) :: "memory");
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < MB_UNROLL; ++u) {
@@ -62,7 +63,7 @@ microbench_kernel(uint32_t *out, int iters, uint32_t seed, long long *cycles) {
             }
         }
     }
-    const long long t1 = clock64();
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1) :: "memory");
     uint32_t s = 0;
 #pragma unroll
     for (int j = 0; j < MB_ACC; ++j) s ^= acc[j];

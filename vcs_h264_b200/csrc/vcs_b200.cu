@@ -377,7 +377,13 @@ int vcs_destroy(vcs_ctx *ctx) {
 
 int vcs_set_stream(vcs_ctx *ctx, void *cuda_stream) {
     if (!ctx) return VCS_E_INVALID;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;   // 0 is CUDA's legacy default stream, taken literally
+    return VCS_OK;
+}
+
+int vcs_use_own_stream(vcs_ctx *ctx) {
+    if (!ctx) return VCS_E_INVALID;
+    ctx->stream = ctx->own_stream;
     return VCS_OK;
 }
 

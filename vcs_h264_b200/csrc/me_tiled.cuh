@@ -37,7 +37,7 @@ struct TiledCfg {
     static constexpr int BS = BS_;            // macroblock size (8 or 16)
     static constexpr int ND = ND_;            // offsets per chunk and axis (9, 17 or 33)
     static constexpr int MX = ND_ == 9 ? 7 : 5;   // macroblocks per tile, x
-    static constexpr int MY = ND_ == 9 ? 4 : 3;   // macroblocks per tile, y
+    static constexpr int MY = ND_ == 9 ? 2 : 3;   // macroblocks per tile, y
     static constexpr int NMB = MX * MY;
     static constexpr int ITEMS = NMB * ND;    // (macroblock, dx) pairs
     static constexpr int THREADS = (ITEMS + 127) / 128 * 128;
@@ -46,12 +46,13 @@ struct TiledCfg {
     static constexpr int WR = ND - 1 + BS * MY;   // window rows
     static constexpr int RP = (WR - 16 + 31) / 32 * 32 + 16;  // padded rows, = 16 (mod 32)
     // raw stage: words per row; multiple of 4 with RAWW/4 odd (conflict-free LDS.128 by row)
-    static constexpr int RAW_NEED = (3 + 3 * WPX + 3 + 3) / 4 + 1;
+    // TMA needs a 16-byte aligned global start, so up to 15 bytes precede the window in a raw row
+    static constexpr int RAW_NEED = (15 + 3 * WPX + 3 + 3) / 4 + 1;
     static constexpr int RAWW4 = (RAW_NEED + 3) / 4;
     static constexpr int RAWW = (RAWW4 % 2 ? RAWW4 : RAWW4 + 1) * 4;
-    static constexpr int NC = ((3 + 3 * (BS * (MX - 1) + ND - 1)) >> 2) + WPR;  // word columns of T
+    static constexpr int NC = ((15 + 3 * (BS * (MX - 1) + ND - 1)) >> 2) + WPR;  // word columns of T
     static constexpr int PS = (NC * RP + 31) / 32 * 32 + 4;  // phase stride, = 4 (mod 32)
-    static constexpr int CURW = (MX * WPR + 3) / 4 * 4;  // words per row of the raw macroblock tile (TMA: 16 B multiple)
+    static constexpr int CURW = (MX * WPR + 3 + 3) / 4 * 4;  // words per raw macroblock-tile row (16 B aligned start + multiple)
     static constexpr int CURR = MY * BS;      // rows of it
     // shared memory carve-up (bytes)
     static constexpr size_t OFF_T = 0;
@@ -120,7 +121,7 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, ui
 }
 __device__ __forceinline__ uint4 lds128(const uint32_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 
-__device__ __forceinline__ int floordiv4(int v) { return v >> 2; }  // arithmetic shift = floor for negatives
+__device__ __forceinline__ int floordiv16(int v) { return v >> 4; }  // arithmetic shift = floor for negatives
 
 // ---- the kernel ---------------------------------------------------------------------------------
 template <class C, int METRIC>
@@ -168,10 +169,11 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
         const int b = (int)(s & 1);
         const int xw0 = tx * MX * BS + a.lo + cx * ND, yw0 = ty * C::MY * BS + a.lo + cy * ND;
         mbar_expect_tx(&sBar[b], (uint32_t)(C::RAWW * C::WR * 4 + C::CURW * C::CURR * 4));
-        tma_load_3d(smem + C::OFF_RAW + b * C::SZ_RAW_AL, &tm_ref, &sBar[b], floordiv4(3 * xw0), yw0,
+        // the innermost TMA coordinate must land on a 16-byte boundary: align down, keep the remainder
+        tma_load_3d(smem + C::OFF_RAW + b * C::SZ_RAW_AL, &tm_ref, &sBar[b], 4 * floordiv16(3 * xw0), yw0,
                     p / a.ppg);
-        tma_load_4d(smem + C::OFF_CRAW + b * C::SZ_CRAW_AL, &tm_cur, &sBar[b], tx * MX * WPR, ty * C::MY * BS,
-                    p % a.ppg, p / a.ppg);
+        tma_load_4d(smem + C::OFF_CRAW + b * C::SZ_CRAW_AL, &tm_cur, &sBar[b], 4 * floordiv16(tx * MX * BS * 3),
+                    ty * C::MY * BS, p % a.ppg, p / a.ppg);
     };
 
     if (tid == 0) {
@@ -195,7 +197,8 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
         unit_geom(s, p, tx, ty, cy, cx, first, last);
         const int b = (int)(s & 1);
         const int xw0 = tx * MX * BS + a.lo + cx * ND, yw0 = ty * C::MY * BS + a.lo + cy * ND;
-        const int ao = 3 * xw0 - 4 * floordiv4(3 * xw0);   // byte offset of the window inside raw word 0
+        const int ao = 3 * xw0 - 16 * floordiv16(3 * xw0);   // byte offset of the window inside a raw row
+        const int cao = (tx * MX * BS * 3 - 16 * floordiv16(tx * MX * BS * 3)) >> 2;   // word offset of the MB tile
         mbar_wait(&sBar[b], (uint32_t)((s >> 1) & 1));
 
         // ---- re-lay the raw window: 4 byte phases, transposed [phase][word col][row] ----------
@@ -227,7 +230,7 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
             const uint32_t *craw = reinterpret_cast<const uint32_t *>(smem + C::OFF_CRAW + b * C::SZ_CRAW_AL);
             for (int k = tid; k < NMB * WPR * BS; k += C::THREADS) {
                 const int v = k % BS, w = (k / BS) % WPR, m = k / (BS * WPR);
-                const uint32_t c = craw[((m / MX) * BS + v) * C::CURW + (m % MX) * WPR + w];
+                const uint32_t c = craw[((m / MX) * BS + v) * C::CURW + cao + (m % MX) * WPR + w];
                 if (METRIC == 0) { sCurT[k] = c & ~Hm; sCurH[k] = c & Hm; }
                 else sCurT[k] = c;
             }

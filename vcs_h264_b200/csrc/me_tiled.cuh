@@ -52,7 +52,8 @@ struct TiledCfg {
     static constexpr int RAWW = (RAWW4 % 2 ? RAWW4 : RAWW4 + 1) * 4;
     static constexpr int NC = ((15 + 3 * (BS * (MX - 1) + ND - 1)) >> 2) + WPR;  // word columns of T
     static constexpr int PS = (NC * RP + 31) / 32 * 32 + 4;  // phase stride, = 4 (mod 32)
-    static constexpr int CURW = (MX * WPR + 3 + 3) / 4 * 4;  // words per raw macroblock-tile row (16 B aligned start + multiple)
+    static constexpr int CURW4 = (MX * WPR + 3 + 3) / 4;
+    static constexpr int CURW = (CURW4 % 2 ? CURW4 : CURW4 + 1) * 4;  // words per raw MB-tile row: 16 B multiple, CURW/4 odd
     static constexpr int CURR = MY * BS;      // rows of it
     // shared memory carve-up (bytes)
     static constexpr size_t OFF_T = 0;
@@ -78,6 +79,7 @@ struct TiledArgs {
     int ncy, ncx;              // chunks of the offset range per axis
     int zchunk;                // index (cy*ncx+cx) of the chunk holding offset (0,0), or 0
     int npairs, ppg;
+    uint32_t zero;             // always 0; opaque to the compiler (pipe balancing, see the wrap8 loop)
     int16_t *mv;
     uint32_t *cost;
     uint8_t *flags;
@@ -130,6 +132,7 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
                 const TiledArgs a) {
     constexpr int BS = C::BS, ND = C::ND, MX = C::MX, NMB = C::NMB, WPR = C::WPR, RP = C::RP, PS = C::PS;
     constexpr uint32_t Hm = 0x80808080u;
+    const uint32_t zero = a.zero;
     extern __shared__ __align__(128) unsigned char smem[];
     uint32_t *sT = reinterpret_cast<uint32_t *>(smem + C::OFF_T);
     uint32_t *sCurT = reinterpret_cast<uint32_t *>(smem + C::OFF_CURT);           // SAD: c ; wrap8: c & ~H
@@ -228,6 +231,8 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
             }
             // macroblocks: raw [row][word] -> [mb][w][v]
             const uint32_t *craw = reinterpret_cast<const uint32_t *>(smem + C::OFF_CRAW + b * C::SZ_CRAW_AL);
+            // lanes run along v (rows): conflict-free stores; a row pitch of CURW words with CURW/4 odd
+            // keeps the strided reads at <= 2-way
             for (int k = tid; k < NMB * WPR * BS; k += C::THREADS) {
                 const int v = k % BS, w = (k / BS) % WPR, m = k / (BS * WPR);
                 const uint32_t c = craw[((m / MX) * BS + v) * C::CURW + cao + (m % MX) * WPR + w];
@@ -319,12 +324,25 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
                         const int r = 4 * rq + e;        // window row relative to the macroblock row
                         if (r < ROWS) {
                             if (METRIC == 0) {
-                                const uint32_t r1 = rr[e] | Hm, r2 = ~rr[e] & Hm;
+                                // r1, r2 are pinned with asm so ptxas keeps ONE 3-input xor per use
+                                // (it otherwise re-derives r2 inside every use: 2 LOP3 on the ALU pipe)
+                                uint32_t r1, r2;
+                                asm("lop3.b32 %0, %1, %2, %2, 0xfc;" : "=r"(r1) : "r"(rr[e]), "r"(Hm));   // r | H
+                                asm("lop3.b32 %0, %1, %2, %2, 0x0c;" : "=r"(r2) : "r"(rr[e]), "r"(Hm));   // ~r & H
 #pragma unroll
                                 for (int d = 0; d < ND; ++d) {
                                     const int v = r - d;
                                     if (v >= 0 && v < BS) {
-                                        const uint32_t z = (r1 - c[v]) ^ r2 ^ chh[v];
+                                        // the subtract can issue on either pipe (IADD3 = ALU, IMAD.IADD =
+                                        // FMA); ptxas sends them all to FMA, where IDP.4A also lives.  A third
+                                        // (opaque zero) addend forces IADD3 for 2 of 5 so both pipes fill up.
+                                        uint32_t z;
+                                        if (d % 5 < 2)
+                                            asm("{\n.reg .u32 t;\nsub.u32 t, %1, %2;\nadd.u32 t, t, %5;\n"
+                                                "lop3.b32 %0, t, %3, %4, 0x96;\n}"
+                                                : "=r"(z) : "r"(r1), "r"(c[v]), "r"(r2), "r"(chh[v]), "r"(zero));
+                                        else
+                                            asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(z) : "r"(r1 - c[v]), "r"(r2), "r"(chh[v]));
                                         acc[d] = __dp4a(z, 0x01010101u, acc[d]);
                                     }
                                 }
@@ -436,7 +454,7 @@ int me_tiled_run(MeTiledState &st, cudaStream_t stream, const MeGeom &g, const F
     a.ncy = a.ncx = (nd_total + C::ND - 1) / C::ND;
     a.zchunk = 0;
     if (g.lo <= 0 && g.hi >= 0) { const int cz = (-g.lo) / C::ND; a.zchunk = cz * a.ncx + cz; }
-    a.npairs = npairs; a.ppg = fa.ppg; a.mv = mv; a.cost = cost; a.flags = flags;
+    a.npairs = npairs; a.ppg = fa.ppg; a.zero = 0; a.mv = mv; a.cost = cost; a.flags = flags;
     const long long ntiles = (long long)a.tiles_x * a.tiles_y * npairs;
     long long grid = (long long)sm_count * st.occupancy[bi][ni][METRIC];
     if (grid > ntiles) grid = ntiles;

@@ -15,11 +15,24 @@
 // uint8 image is the C cast (uint8)(int64)x.  The file is compiled with -fmad=false and uses
 // explicit __fma_rn so no other contraction can occur.
 //
-// Work decomposition: one CTA per tile of 8 rows x 128 pixels (16 blocks x 3 channels), 384
-// threads = (block-channel, lane-in-block).  Column pass and row pass of each transform are
-// thread-local 8-term chains on shared-memory tiles; all global traffic is staged through
-// shared memory so it is coalesced.  The kernel is HBM-bound: per pixel it reads cur 3 B +
-// ref 3 B and writes coefficients (24 B f64 | 6 B int16) and 3 B of reconstruction.
+// Work decomposition: WARP-private tiles, no CTA barriers.  A warp owns a tile of 8 rows x 32 pixels
+// (4 blocks x 3 channels) and walks through the stages with __syncwarp() only, so the warps of an SM
+// are always in different stages and hide each other's latencies:
+//   A  lane = one 8-pixel group: cur (3 x LDG.64) and the motion-compensated prediction (aligned
+//      words + funnel shift), residual, BGR->YCrCb-128 packed as int8 into shared memory;
+//   B  lane = one pixel column of all 3 channels: 24 inputs in registers, 8 x 3 DFMA chains, every
+//      DCT-matrix constant fetched once for the 3 channels; results in place (doubles, row stride 33);
+//   C  lane = (block, row) of all 3 channels: row pass, quantise, coefficients straight to global
+//      memory (8 int16 = one STG.128 per channel), E = q*Q back in place;
+//   D/E the inverse column and row passes the same way, truncating store into packed bytes;
+//   F  lane = one 8-pixel group: YCrCb->BGR, + prediction, 3 x STG.64.
+// The kernel moves 15 B/px (int16 indices) but is FP64-pipe bound first: 96 DFMA per pixel.
+//
+// Quantiser: the reference computes rint(RN(D/Q)).  For the rounded modes the kernel takes
+// q0 = D * RN(1/Q) (within 2^-40 of the true quotient for |q| < 2^11) and only when q0 lies within
+// 2^-30 of a half-integer falls back to the IEEE divide, so the result is bit-identical while the
+// common path costs a DMUL.  The un-rounded mode (the reference's inter path, DCTcompressor.py:71)
+// always uses the IEEE divide.
 #pragma once
 #include "common.cuh"
 
@@ -27,11 +40,14 @@ namespace vcs {
 
 __constant__ double c_dct[64];  // _dctMatrix(), row-major, computed on the host with libm
 
-constexpr int DCT_TILE_W = 128;                 // pixels per tile row
-constexpr int DCT_THREADS = 3 * (DCT_TILE_W / 8) * 8;  // 384
-constexpr int DCT_RS = DCT_TILE_W + 1;          // padded row stride (doubles): conflict-free
-constexpr size_t DCT_SMEM_BYTES = (size_t)(2 * 3 * 8 * DCT_RS + 192) * sizeof(double) +
-                                  2 * 8 * DCT_TILE_W * 3;
+constexpr int DCT_TILE_W = 32;                        // pixels per warp tile row (4 blocks)
+constexpr int DCT_WARPS = 4;                          // warps per CTA, each with a private tile
+constexpr int DCT_THREADS = 32 * DCT_WARPS;
+constexpr int DCT_RS = DCT_TILE_W + 1;                // row stride of the double tiles: conflict-free
+constexpr int DCT_X_DOUBLES = 3 * 8 * DCT_RS;         // per-warp transform tile [3][8][RS]
+constexpr int DCT_PLANE = 8 * DCT_TILE_W * 3;         // bytes of one 8 x 32 x 3 byte tile
+constexpr size_t DCT_WARP_BYTES = (size_t)DCT_X_DOUBLES * sizeof(double) + 3 * DCT_PLANE;
+constexpr size_t DCT_SMEM_BYTES = 2 * 192 * sizeof(double) + DCT_WARPS * DCT_WARP_BYTES;
 
 struct DctArgs {
     int H, W;
@@ -50,180 +66,315 @@ struct DctArgs {
     uint8_t *recon;          // [nP][H][W][3] or nullptr
 };
 
-__device__ __forceinline__ double quantise(double d, double q, int coef_mode) {
-    double v = d / q;  // np.true_divide (DCTcompressor.py:71)
-    return coef_mode == 0 ? v : rint(v);  // np.round (dct.py:179)
+// 24 bytes (8 BGR pixels) starting at an arbitrary byte address, as 6 words
+__device__ __forceinline__ void load24(const uint8_t *p, uint32_t w[6]) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    if ((a & 7) == 0) {
+        const uint2 *q = reinterpret_cast<const uint2 *>(p);
+        const uint2 v0 = __ldg(q), v1 = __ldg(q + 1), v2 = __ldg(q + 2);
+        w[0] = v0.x; w[1] = v0.y; w[2] = v1.x; w[3] = v1.y; w[4] = v2.x; w[5] = v2.y;
+        return;
+    }
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+    const int sh = (int)(a & 3) * 8;
+    uint32_t r[7];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) r[k] = __ldg(q + k);
+    r[6] = sh ? __ldg(q + 6) : 0u;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) w[k] = sh ? __funnelshift_r(r[k], r[k + 1], sh) : r[k];
 }
 
-__global__ void __launch_bounds__(DCT_THREADS)
-dct_stage_kernel(DctArgs a) {
+__device__ __forceinline__ uint32_t byte_of(const uint32_t *w, int k) { return (w[k >> 2] >> (8 * (k & 3))) & 0xffu; }
+
+__global__ void __launch_bounds__(DCT_THREADS, 4)
+dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     extern __shared__ __align__(16) unsigned char dct_smem[];
-    double *s_a = reinterpret_cast<double *>(dct_smem);
-    double *s_b = s_a + 3 * 8 * DCT_RS;
-    double *s_q = s_b + 3 * 8 * DCT_RS;
-    uint8_t *s_pred = reinterpret_cast<uint8_t *>(s_q + 192);
-    uint8_t *s_ycc = s_pred + 8 * DCT_TILE_W * 3;
+    double *s_q = reinterpret_cast<double *>(dct_smem);          // Q [3][64]
+    double *s_rq = s_q + 192;                                    // RN(1/Q)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wbase = dct_smem + 2 * 192 * sizeof(double) + warp * DCT_WARP_BYTES;
+    double *s_x = reinterpret_cast<double *>(wbase);                              // [3][8][RS]
+    uint8_t *s_pred = wbase + DCT_X_DOUBLES * sizeof(double);                     // [8][32*3] prediction (BGR)
+    int8_t *s_in8 = reinterpret_cast<int8_t *>(s_pred + DCT_PLANE);               // [3][8][32] YCrCb-128
+    uint8_t *s_out = reinterpret_cast<uint8_t *>(s_in8 + DCT_PLANE);              // [3][8][32] decoded YCrCb
 
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * DCT_TILE_W, y0 = blockIdx.y * 8, p = blockIdx.z;
-    const int tw = min(DCT_TILE_W, a.W - x0);  // multiple of 8
-    const size_t npix = (size_t)a.H * a.W;
-    const int N = a.nbx * a.nby;
+    const int W = a.W, H = a.H, bs = a.bs, nbx = a.nbx, nby = a.nby;
+    const int forward = a.forward, coef_mode = a.coef_mode;
+    const bool do_inverse = a.inverse && a.recon;
+    const size_t npix = (size_t)H * W;
+    const int N = nbx * nby;
 
-    for (int k = tid; k < 192; k += DCT_THREADS) s_q[k] = a.Q[k];
-
-    const uint8_t *cur = nullptr, *ref = nullptr;
-    if (a.has_fa) {
-        cur = cur_frame(a.fa, p);
-        ref = ref_frame(a.fa, p);
-    } else if (a.img) {
-        cur = a.img + (size_t)p * npix * 3;
+    // stored transposed, [ch][j][i]: in the row passes lanes differ in i, so they read consecutive doubles
+    for (int k = threadIdx.x; k < 192; k += DCT_THREADS) {
+        const double q = a.Q[k];
+        const int ch = k >> 6, i = (k >> 3) & 7, j = k & 7;
+        s_q[ch * 64 + j * 8 + i] = q;
+        s_rq[ch * 64 + j * 8 + i] = 1.0 / q;
     }
-    const int16_t *mv = a.mv ? a.mv + (size_t)p * N * 2 : nullptr;
+    __syncthreads();   // the only CTA-wide barrier
 
-    // ---- 1. gather: pred (MC), residual, BGR->YCrCb, -128 ---------------------------------
-    if (a.forward) {
-        for (int k = tid; k < 8 * DCT_TILE_W; k += DCT_THREADS) {
-            const int r = k / DCT_TILE_W, c = k - r * DCT_TILE_W;
-            if (c >= tw) continue;
-            const int x = x0 + c, y = y0 + r;
-            const uint8_t *cp = cur + ((size_t)y * a.W + x) * 3;
-            int pb = 0, pg = 0, pr = 0;
-            if (mv) {
-                const int mbx = x / a.bs, mby = y / a.bs;
-                if (mbx < a.nbx && mby < a.nby) {  // uncovered border stays 0 (motion.py:45-46)
-                    const int16_t *m = mv + 2 * (mby * a.nbx + mbx);
-                    const uint8_t *rp = ref + ((size_t)(y + m[1]) * a.W + (x + m[0])) * 3;
-                    pb = __ldg(rp); pg = __ldg(rp + 1); pr = __ldg(rp + 2);
+    const int ntx = (W + DCT_TILE_W - 1) / DCT_TILE_W, nty = H / 8;
+    const long long nitems = (long long)ntx * nty * nP;
+    const long long nwarps = (long long)gridDim.x * DCT_WARPS;
+
+    // lane roles
+    const int g_r = lane >> 2, g_c = (lane & 3) * 8;        // stages A/F: 8-pixel group (row, first column)
+    const int rp_i = lane & 7, rp_blk = lane >> 3;          // row passes: row i of block blk
+    const int rbase0 = rp_i * DCT_RS + rp_blk * 8;          // + ch * 8 * RS
+
+    for (long long item = (long long)blockIdx.x * DCT_WARPS + warp; item < nitems; item += nwarps) {
+        const int tx = (int)(item % ntx), ty = (int)((item / ntx) % nty), p = (int)(item / ((long long)ntx * nty));
+        const int x0 = tx * DCT_TILE_W, y0 = ty * 8;
+        const int tw = min(DCT_TILE_W, W - x0);   // multiple of 8
+        const bool g_on = g_c < tw, col_on = lane < tw, row_on = rp_blk * 8 < tw;
+        const uint8_t *cur = nullptr, *ref = nullptr;
+        if (a.has_fa) {
+            cur = cur_frame(a.fa, p);
+            ref = ref_frame(a.fa, p);
+        } else if (a.img) {
+            cur = a.img + (size_t)p * npix * 3;
+        }
+        const int16_t *mv = a.mv ? a.mv + (size_t)p * N * 2 : nullptr;
+
+        // ---- A: gather, residual, colour ------------------------------------------------------------
+        if (g_on) {
+            const int x = x0 + g_c, y = y0 + g_r;
+            uint32_t pw[6] = {0, 0, 0, 0, 0, 0};
+            if (forward) {
+                uint32_t cw[6];
+                load24(cur + ((size_t)y * W + x) * 3, cw);
+                if (mv) {
+                    if (bs % 8 == 0) {   // the group lies inside one macroblock
+                        const int mbx = x / bs, mby = y / bs;
+                        if (mbx < nbx && mby < nby) {   // uncovered border stays 0 (motion.py:45-46)
+                            const int16_t *m = mv + 2 * (mby * nbx + mbx);
+                            load24(ref + ((size_t)(y + m[1]) * W + (x + m[0])) * 3, pw);
+                        }
+                    } else {             // per-pixel gather (block sizes that are not multiples of 8)
+                        for (int u = 0; u < 8; ++u) {
+                            const int mbx = (x + u) / bs, mby = y / bs;
+                            uint32_t b3 = 0;
+                            if (mbx < nbx && mby < nby) {
+                                const int16_t *m = mv + 2 * (mby * nbx + mbx);
+                                const uint8_t *rp = ref + ((size_t)(y + m[1]) * W + (x + u + m[0])) * 3;
+                                b3 = (uint32_t)__ldg(rp) | ((uint32_t)__ldg(rp + 1) << 8) | ((uint32_t)__ldg(rp + 2) << 16);
+                            }
+                            for (int e = 0; e < 3; ++e) s_pred[(g_r * DCT_TILE_W + g_c + u) * 3 + e] = (uint8_t)(b3 >> (8 * e));
+                        }
+                        const uint32_t *sp = reinterpret_cast<const uint32_t *>(s_pred + (g_r * DCT_TILE_W + g_c) * 3);
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) pw[k] = sp[k];
+                    }
+                }
+                // residual wraps mod 256 per byte (motion.py:39) and is then treated as a BGR image
+                uint32_t rw[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) rw[k] = __vsub4(cw[k], pw[k]);
+                uint32_t yv[2] = {0, 0}, crv[2] = {0, 0}, cbv[2] = {0, 0};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int B = byte_of(rw, 3 * u), G = byte_of(rw, 3 * u + 1), R = byte_of(rw, 3 * u + 2);
+                    int Y, Cr, Cb;
+                    bgr2ycrcb(B, G, R, Y, Cr, Cb);
+                    yv[u >> 2] |= (uint32_t)((Y - 128) & 0xff) << (8 * (u & 3));
+                    crv[u >> 2] |= (uint32_t)((Cr - 128) & 0xff) << (8 * (u & 3));
+                    cbv[u >> 2] |= (uint32_t)((Cb - 128) & 0xff) << (8 * (u & 3));
+                }
+                *reinterpret_cast<uint2 *>(s_in8 + (0 * 8 + g_r) * DCT_TILE_W + g_c) = make_uint2(yv[0], yv[1]);
+                *reinterpret_cast<uint2 *>(s_in8 + (1 * 8 + g_r) * DCT_TILE_W + g_c) = make_uint2(crv[0], crv[1]);
+                *reinterpret_cast<uint2 *>(s_in8 + (2 * 8 + g_r) * DCT_TILE_W + g_c) = make_uint2(cbv[0], cbv[1]);
+            } else if (a.pred_in) {
+                load24(a.pred_in + (size_t)p * npix * 3 + ((size_t)y * W + x) * 3, pw);
+            }
+            uint32_t *sp = reinterpret_cast<uint32_t *>(s_pred + (g_r * DCT_TILE_W + g_c) * 3);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sp[k] = pw[k];
+        }
+        __syncwarp();
+
+        const size_t gidx0 = (size_t)p * 3 * npix + (size_t)(y0 + rp_i) * W + x0 + rp_blk * 8;   // + ch * npix
+        if (forward) {
+            // ---- B: column pass  T = C . X  (T[i][j] = sum_k C[i][k] X[k][j]), 3 channels per lane ------
+            if (col_on) {
+                double xk[3][8];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) xk[ch][k] = (double)(int)s_in8[(ch * 8 + k) * DCT_TILE_W + lane];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const double c = c_dct[i * 8 + k];
+                        s0 = __fma_rn(c, xk[0][k], s0);
+                        s1 = __fma_rn(c, xk[1][k], s1);
+                        s2 = __fma_rn(c, xk[2][k], s2);
+                    }
+                    s_x[(0 * 8 + i) * DCT_RS + lane] = s0;
+                    s_x[(1 * 8 + i) * DCT_RS + lane] = s1;
+                    s_x[(2 * 8 + i) * DCT_RS + lane] = s2;
                 }
             }
-            s_pred[3 * k] = (uint8_t)pb; s_pred[3 * k + 1] = (uint8_t)pg; s_pred[3 * k + 2] = (uint8_t)pr;
-            // residual wraps mod 256 (motion.py:39) and is then treated as a BGR image
-            const int B = (uint8_t)(__ldg(cp) - pb), G = (uint8_t)(__ldg(cp + 1) - pg),
-                      R = (uint8_t)(__ldg(cp + 2) - pr);
-            int Y, Cr, Cb;
-            bgr2ycrcb(B, G, R, Y, Cr, Cb);
-            s_a[(0 * 8 + r) * DCT_RS + c] = (double)(Y - 128);
-            s_a[(1 * 8 + r) * DCT_RS + c] = (double)(Cr - 128);
-            s_a[(2 * 8 + r) * DCT_RS + c] = (double)(Cb - 128);
-        }
-    } else {
-        // inverse-only: coefficient planes in, optional pred image
-        for (int k = tid; k < 3 * 8 * DCT_TILE_W; k += DCT_THREADS) {
-            const int ch = k / (8 * DCT_TILE_W), rem = k - ch * 8 * DCT_TILE_W;
-            const int r = rem / DCT_TILE_W, c = rem - r * DCT_TILE_W;
-            if (c >= tw) continue;
-            const size_t gi = ((size_t)p * 3 + ch) * npix + (size_t)(y0 + r) * a.W + x0 + c;
-            double v = a.coef_mode == 2 ? (double)((const int16_t *)a.coef)[gi]
-                                        : ((const double *)a.coef)[gi];
-            s_a[(ch * 8 + r) * DCT_RS + c] = v;
-        }
-        for (int k = tid; k < 8 * DCT_TILE_W * 3; k += DCT_THREADS) {
-            const int r = k / (DCT_TILE_W * 3), cb = k - r * DCT_TILE_W * 3;
-            uint8_t v = 0;
-            if (a.pred_in && cb < tw * 3)
-                v = a.pred_in[(size_t)p * npix * 3 + ((size_t)(y0 + r) * a.W + x0) * 3 + cb];
-            s_pred[k] = v;
-        }
-    }
-    __syncthreads();
-
-    // thread roles for the transform passes
-    const int colpass_ch = tid / DCT_TILE_W, colpass_c = tid - colpass_ch * DCT_TILE_W;  // (ch, column)
-    // row pass: lane = i + 8 * (blk & 3) keeps the 8-byte shared accesses conflict-free
-    const int rp_ch = tid / 128, rp_rem = tid - rp_ch * 128;
-    const int rp_i = rp_rem & 7, rp_blk = ((rp_rem >> 5) << 2) | ((rp_rem >> 3) & 3);
-    const bool col_on = colpass_c < tw, row_on = rp_blk * 8 < tw;
-
-    if (a.forward) {
-        // ---- 2. column pass  T = C . X  (T[i][j] = sum_k C[i][k] X[k][j]) ------------------
-        if (col_on) {
-            double xk[8];
+            __syncwarp();
+            // ---- C: row pass  D = T . C^T  (D[i][j] = sum_k T[i][k] C[j][k]); quantise; store ------------
+            if (row_on) {
+                double tk[3][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) xk[k] = s_a[(colpass_ch * 8 + k) * DCT_RS + colpass_c];
+                for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                double s = 0.0;
+                    for (int k = 0; k < 8; ++k) tk[ch][k] = s_x[ch * 8 * DCT_RS + rbase0 + k];
+                uint32_t pk[3][4];
+                double dprev[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-                for (int k = 0; k < 8; ++k) s = __fma_rn(c_dct[i * 8 + k], xk[k], s);
-                s_b[(colpass_ch * 8 + i) * DCT_RS + colpass_c] = s;
+                for (int j = 0; j < 8; ++j) {
+                    double s[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const double c = c_dct[j * 8 + k];
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) s[ch] = __fma_rn(tk[ch][k], c, s[ch]);
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const double Q = s_q[ch * 64 + j * 8 + rp_i];
+                        double v;
+                        if (coef_mode == 0) {
+                            v = s[ch] / Q;                                 // np.true_divide (DCTcompressor.py:71)
+                        } else {
+                            const double q0 = s[ch] * s_rq[ch * 64 + j * 8 + rp_i];
+                            v = rint(q0);                                  // np.round (dct.py:179) of RN(s/Q):
+                            if (fabs(fabs(q0 - v) - 0.5) < 9.313225746154785e-10)   // 2^-30 of a half-integer
+                                v = rint(s[ch] / Q);                       // -> the exact quotient decides
+                        }
+                        if (a.coef) {
+                            if (coef_mode == 2) {
+                                const uint32_t h = (uint32_t)(uint16_t)(int16_t)(int)v;
+                                if (j & 1) pk[ch][j >> 1] |= h << 16; else pk[ch][j >> 1] = h;
+                            } else if (j & 1) {
+                                *reinterpret_cast<double2 *>(reinterpret_cast<double *>(a.coef) + gidx0 + ch * npix + j - 1) =
+                                    make_double2(dprev[ch], v);
+                            } else {
+                                dprev[ch] = v;
+                            }
+                        }
+                        if (do_inverse) s_x[ch * 8 * DCT_RS + rbase0 + j] = v * Q;   // E = blk * Q (DCTcompressor.py:86)
+                    }
+                }
+                if (a.coef && coef_mode == 2) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        *reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(a.coef) + gidx0 + ch * npix) =
+                            make_uint4(pk[ch][0], pk[ch][1], pk[ch][2], pk[ch][3]);
+                }
+            }
+        } else if (do_inverse && row_on) {
+            // inverse-only: E = coefficient planes * Q
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                double qv[8];
+                if (coef_mode == 2) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const int16_t *>(a.coef) + gidx0 + ch * npix);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) qv[j] = (double)(int)(int16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
+                } else {
+                    const double *o = reinterpret_cast<const double *>(a.coef) + gidx0 + ch * npix;
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const double2 v = *reinterpret_cast<const double2 *>(o + j);
+                        qv[j] = v.x; qv[j + 1] = v.y;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s_x[ch * 8 * DCT_RS + rbase0 + j] = qv[j] * s_q[ch * 64 + j * 8 + rp_i];
             }
         }
-        __syncthreads();
-        // ---- 3. row pass  D = T . C^T  (D[i][j] = sum_k T[i][k] C[j][k]);  / Q -------------
-        if (row_on) {
-            double tk[8];
-            const int base = (rp_ch * 8 + rp_i) * DCT_RS + rp_blk * 8;
+        if (do_inverse) {
+            __syncwarp();
+            // ---- D: inverse column pass  T' = C^T . E  (T'[i][j] = sum_k C[k][i] E[k][j]) ---------------------
+            if (col_on) {
+                double ek[3][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) tk[k] = s_b[base + k];
+                for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                double s = 0.0;
+                    for (int k = 0; k < 8; ++k) ek[ch][k] = s_x[(ch * 8 + k) * DCT_RS + lane];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) s = __fma_rn(tk[k], c_dct[j * 8 + k], s);
-                s_a[base + j] = quantise(s, s_q[rp_ch * 64 + rp_i * 8 + j], a.coef_mode);
+                for (int i = 0; i < 8; ++i) {
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const double c = c_dct[k * 8 + i];
+                        s0 = __fma_rn(c, ek[0][k], s0);
+                        s1 = __fma_rn(c, ek[1][k], s1);
+                        s2 = __fma_rn(c, ek[2][k], s2);
+                    }
+                    s_x[(0 * 8 + i) * DCT_RS + lane] = s0;
+                    s_x[(1 * 8 + i) * DCT_RS + lane] = s1;
+                    s_x[(2 * 8 + i) * DCT_RS + lane] = s2;
+                }
+            }
+            __syncwarp();
+            // ---- E: inverse row pass  P = T' . C ; truncating uint8 store ; +128 ---------------------------------
+            if (row_on) {
+                double tk[3][8];
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) tk[ch][k] = s_x[ch * 8 * DCT_RS + rbase0 + k];
+                uint32_t w[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    double s[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const double c = c_dct[k * 8 + j];
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) s[ch] = __fma_rn(tk[ch][k], c, s[ch]);
+                    }
+                    // float64 -> uint8 store (DCTcompressor.py:81,88): truncate toward zero, low 8 bits; then +128
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        w[ch][j >> 2] |= (((uint32_t)(long long)s[ch] + 128u) & 0xffu) << (8 * (j & 3));
+                }
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+                    *reinterpret_cast<uint2 *>(s_out + (ch * 8 + rp_i) * DCT_TILE_W + rp_blk * 8) = make_uint2(w[ch][0], w[ch][1]);
+            }
+            __syncwarp();
+            // ---- F: YCrCb -> BGR, + pred (wrap) -----------------------------------------------------------------------
+            if (g_on) {
+                const uint2 yv = *reinterpret_cast<const uint2 *>(s_out + (0 * 8 + g_r) * DCT_TILE_W + g_c);
+                const uint2 crv = *reinterpret_cast<const uint2 *>(s_out + (1 * 8 + g_r) * DCT_TILE_W + g_c);
+                const uint2 cbv = *reinterpret_cast<const uint2 *>(s_out + (2 * 8 + g_r) * DCT_TILE_W + g_c);
+                const uint32_t *sp = reinterpret_cast<const uint32_t *>(s_pred + (g_r * DCT_TILE_W + g_c) * 3);
+                uint32_t ow[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int sh = 8 * (u & 3);
+                    const int Y = ((u < 4 ? yv.x : yv.y) >> sh) & 0xff, Cr = ((u < 4 ? crv.x : crv.y) >> sh) & 0xff,
+                              Cb = ((u < 4 ? cbv.x : cbv.y) >> sh) & 0xff;
+                    int B, G, R;
+                    ycrcb2bgr(Y, Cr, Cb, B, G, R);
+                    ow[(3 * u) >> 2] |= (uint32_t)B << (8 * ((3 * u) & 3));
+                    ow[(3 * u + 1) >> 2] |= (uint32_t)G << (8 * ((3 * u + 1) & 3));
+                    ow[(3 * u + 2) >> 2] |= (uint32_t)R << (8 * ((3 * u + 2) & 3));
+                }
+                uint32_t ov[6];   // pred + decoded, uint8 wrap (decoder.py:57)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) ov[k] = __vadd4(ow[k], sp[k]);
+                uint8_t *ob = a.recon + (size_t)p * npix * 3 + ((size_t)(y0 + g_r) * W + x0 + g_c) * 3;
+                if ((reinterpret_cast<uintptr_t>(ob) & 7) == 0) {
+                    uint2 *op = reinterpret_cast<uint2 *>(ob);
+                    op[0] = make_uint2(ov[0], ov[1]); op[1] = make_uint2(ov[2], ov[3]); op[2] = make_uint2(ov[4], ov[5]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 24; ++k) ob[k] = (uint8_t)(ov[k >> 2] >> (8 * (k & 3)));
+                }
             }
         }
-        __syncthreads();
-        // ---- 4. coalesced coefficient store ------------------------------------------------
-        if (a.coef) {
-            for (int k = tid; k < 3 * 8 * DCT_TILE_W; k += DCT_THREADS) {
-                const int ch = k / (8 * DCT_TILE_W), rem = k - ch * 8 * DCT_TILE_W;
-                const int r = rem / DCT_TILE_W, c = rem - r * DCT_TILE_W;
-                if (c >= tw) continue;
-                const size_t gi = ((size_t)p * 3 + ch) * npix + (size_t)(y0 + r) * a.W + x0 + c;
-                const double v = s_a[(ch * 8 + r) * DCT_RS + c];
-                if (a.coef_mode == 2) ((int16_t *)a.coef)[gi] = (int16_t)(int)v;
-                else ((double *)a.coef)[gi] = v;
-            }
-        }
-    }
-    if (!a.inverse || !a.recon) return;
-
-    // ---- 5. dequantise + column pass  T' = C^T . E  (T'[i][j] = sum_k C[k][i] E[k][j]) ------
-    if (col_on) {
-        double ek[8];
-        const int j = colpass_c & 7;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // np.multiply(block, Q) (DCTcompressor.py:86)
-            ek[k] = s_a[(colpass_ch * 8 + k) * DCT_RS + colpass_c] * s_q[colpass_ch * 64 + k * 8 + j];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s = __fma_rn(c_dct[k * 8 + i], ek[k], s);
-            s_b[(colpass_ch * 8 + i) * DCT_RS + colpass_c] = s;
-        }
-    }
-    __syncthreads();
-    // ---- 6. row pass  P = T' . C ; truncating uint8 store ; +128 -----------------------------
-    if (row_on) {
-        double tk[8];
-        const int base = (rp_ch * 8 + rp_i) * DCT_RS + rp_blk * 8;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) tk[k] = s_b[base + k];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s = __fma_rn(tk[k], c_dct[k * 8 + j], s);
-            // float64 -> uint8 store (DCTcompressor.py:81,88): truncate toward zero, low 8 bits
-            const uint8_t p8 = (uint8_t)(long long)s;
-            s_ycc[(rp_i * DCT_TILE_W + rp_blk * 8 + j) * 3 + rp_ch] = (uint8_t)(p8 + 128);
-        }
-    }
-    __syncthreads();
-    // ---- 7. YCrCb -> BGR, + pred (wrap), coalesced store -------------------------------------
-    uint8_t *recon = a.recon + (size_t)p * npix * 3;
-    for (int k = tid; k < 8 * DCT_TILE_W; k += DCT_THREADS) {
-        const int r = k / DCT_TILE_W, c = k - r * DCT_TILE_W;
-        if (c >= tw) continue;
-        int B, G, R;
-        ycrcb2bgr(s_ycc[3 * k], s_ycc[3 * k + 1], s_ycc[3 * k + 2], B, G, R);
-        uint8_t *op = recon + ((size_t)(y0 + r) * a.W + x0 + c) * 3;
-        op[0] = (uint8_t)(B + s_pred[3 * k]);
-        op[1] = (uint8_t)(G + s_pred[3 * k + 1]);
-        op[2] = (uint8_t)(R + s_pred[3 * k + 2]);
+        __syncwarp();   // the next item reuses this warp's tiles
     }
 }
 

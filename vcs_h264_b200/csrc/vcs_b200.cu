@@ -167,8 +167,11 @@ int launch_dct(vcs_ctx *ctx, cudaStream_t st, DctArgs &a, int nP) {
     if (a.coef_mode < 0 || a.coef_mode > 2) return fail(ctx, VCS_E_INVALID, "coef_mode %d", a.coef_mode);
     if (nP <= 0) return VCS_OK;
     a.Q = ctx->d_Q;
-    dim3 grid((a.W + DCT_TILE_W - 1) / DCT_TILE_W, a.H / 8, nP);
-    dct_stage_kernel<<<grid, DCT_THREADS, DCT_SMEM_BYTES, st>>>(a);
+    // persistent warps: 4 CTAs of 4 warps per SM, each warp walks 8x32-pixel tiles
+    const long long nitems = (long long)((a.W + DCT_TILE_W - 1) / DCT_TILE_W) * (a.H / 8) * nP;
+    long long grid = (long long)ctx->sm_count * 4;
+    if (grid * DCT_WARPS > nitems) grid = (nitems + DCT_WARPS - 1) / DCT_WARPS;
+    dct_stage_kernel<<<(unsigned)grid, DCT_THREADS, DCT_SMEM_BYTES, st>>>(a, nP);
     CK(ctx, cudaGetLastError());
     ctx->launches += 1;
     return VCS_OK;

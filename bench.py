@@ -96,6 +96,13 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def make_clip(seed):
     from vcs_h264_b200 import synth
     return synth.clip(T, H, W, seed=seed)
@@ -114,13 +121,13 @@ def run_reference(args, rank, world):
     clip = make_clip(1234)[:sample_frames]
     prm = orc.symmetric_search_params(R)
     Q = orc.qtables(QF)
-    cores = orc.max_threads()
+    cores = host_cores()          # explicit: torchrun exports OMP_NUM_THREADS=1
 
     def step():
         for t in range(sample_frames):
             if t % GOP:
                 orc.encode_p(clip[t], clip[(t // GOP) * GOP], BS, metric=orc.METRIC_WRAP8,
-                             static_thr=STATIC_THR, Q=Q, round_mode=1, simd=True, nthreads=0, **prm)
+                             static_thr=STATIC_THR, Q=Q, round_mode=1, simd=True, nthreads=cores, **prm)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -157,17 +164,18 @@ def cpu_baseline_sample(min_seconds=10.0):
     clip = make_clip(1234)
     prm = orc.symmetric_search_params(R)
     Q = orc.qtables(QF)
+    cores = host_cores()
     t0 = time.perf_counter()
     frames = passes = 0
     while time.perf_counter() - t0 < min_seconds:
         for t in range(T):
             if t % GOP:
                 orc.encode_p(clip[t], clip[(t // GOP) * GOP], BS, metric=orc.METRIC_WRAP8,
-                             static_thr=STATIC_THR, Q=Q, round_mode=1, simd=True, nthreads=0, **prm)
+                             static_thr=STATIC_THR, Q=Q, round_mode=1, simd=True, nthreads=cores, **prm)
             frames += 1
         passes += 1
     dt = time.perf_counter() - t0
-    return {"value": frames / dt, "unit": "frames/s", "cores": orc.max_threads(), "kind": "port",
+    return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": f"{passes} pass(es) over the same 60-frame clip ({frames} frames, I-frames free), "
                       f"oracle/vcs_oracle.c: SSE2 costs, OpenMP over macroblocks, {dt:.1f} s"}
 
@@ -183,6 +191,7 @@ def run_b200(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -211,12 +220,13 @@ def run_b200(args, rank, world, local_rank):
                            metric=metric, static_thr=STATIC_THR, coef_mode=v.COEF_I16_RINT, device=local_rank)
         ctx = ce.ctx
         dout = ce.alloc_device_outputs(T, want_coef=True, want_recon=True)
-        gather = [torch.empty_like(dout["mv"]) for _ in range(world)] if dist is not None else None
+        mv_bytes = dout["mv"].view(torch.uint8)           # NCCL carries bytes (torch has no int16 NCCL type)
+        gather = [torch.empty_like(mv_bytes) for _ in range(world)] if dist is not None else None
 
         def step():
             ce.encode_device(dev_in, dout, stream)
             if gather is not None:                       # per-shard results -> every rank (NCCL)
-                dist.all_gather(gather, dout["mv"])
+                dist.all_gather(gather, mv_bytes)
 
         for _ in range(args.warmup):
             step()

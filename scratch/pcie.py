@@ -1,0 +1,17 @@
+import torch, time
+n = 512 << 20
+h = torch.empty(n, dtype=torch.uint8).pin_memory(); d = torch.empty(n, dtype=torch.uint8, device="cuda")
+h2 = torch.empty(n, dtype=torch.uint8).pin_memory(); d2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+for name, fn in (("H2D", lambda: d.copy_(h, non_blocking=True)), ("D2H", lambda: h.copy_(d, non_blocking=True))):
+    fn(); torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(5): fn()
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t) / 5
+    print(name, f"{n / dt / 1e9:.1f} GB/s")
+torch.cuda.synchronize(); t = time.perf_counter()
+for _ in range(5):
+    with torch.cuda.stream(s1): d.copy_(h, non_blocking=True)
+    with torch.cuda.stream(s2): h2.copy_(d2, non_blocking=True)
+torch.cuda.synchronize(); dt = (time.perf_counter() - t) / 5
+print("duplex each", f"{n / dt / 1e9:.1f} GB/s")

@@ -167,6 +167,20 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
                          int gop_len, int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags,
                          void *coef, uint8_t *recon);
 
+/* ---- decoder side: Decoder._reconstruct_P_frame over a clip (decoder.py:52-69) --------------------- */
+/* ref_frames: the ORIGINAL I-frames only, uint8 [nG][H][W][3] (Decoder.ref_frames); mv / coef indexed by
+ * P-frame ordinal as the encoder wrote them; recon: uint8 [nP][H][W][3] = MC(ref, mv) + decompress(coef). */
+int vcs_decode_clip_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_frames, int T,
+                        int gop_len, const int16_t *mv, int coef_mode, const void *coef,
+                        uint8_t *recon);
+int vcs_decode_clip_host(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_frames, int T,
+                         int gop_len, const int16_t *mv, int coef_mode, const void *coef,
+                         uint8_t *recon);
+/* number of non-zero coefficients among n elements of a DEVICE coefficient buffer: the numerator of the
+ * sparsity print of DCTCompression/dct.py:188-191 (sparsity = 1 - count / n) */
+int vcs_count_nonzero_dev(vcs_ctx *ctx, int coef_mode, const void *coef, size_t n,
+                          unsigned long long *count_host);
+
 /* ---- measurement support ------------------------------------------------------------------ */
 /* Register-only issue-rate microbenchmarks that define the INT32-pipe roofline on the box the
  * bench runs on.  which: 0 VABSDIFF4.U8.ACC, 1 IADD3, 2 LOP3, 3 IMAD, 4 IDP.4A,

@@ -275,3 +275,42 @@ def test_error_behaviour(vcs):
     mp = vcs.MotionProcessor(8, [64, 64])
     with pytest.raises(c.VcsError):                      # MV pointing outside the frame
         mp.reconstruct_from_motion_vectors([[-100, 0]] * 64, buf, mp._block_coords().tolist())
+
+
+@pytest.mark.parametrize("coef_mode", [0, 2])
+def test_clip_decoder_roundtrip(vcs, orc, coef_mode):
+    """Decoder side for a whole clip (decoder.py:52-69): MC from the original I-frames + decompress
+    + wrap add == the encoder's own reconstruction == the oracle, bit for bit (host and device)."""
+    import torch
+    from vcs_h264_b200 import synth
+    T, H, W, bs, R, g = 9, 64, 96, 16, 8, 4
+    clip = synth.clip(T, H, W, seed=41, margin=32)
+    ce = vcs.ClipEncoder([H, W], block_size=bs, search="full", search_range=R, gop_len=g, coef_mode=coef_mode)
+    enc = ce.encode_host(clip, want_coef=True, want_recon=True)
+    refs = np.ascontiguousarray(clip[::g])
+    cd = vcs.ClipDecoder([H, W], block_size=bs, gop_len=g, coef_mode=coef_mode)
+    dec = cd.decode_host(refs, np.asarray(enc["mv"]), np.asarray(enc["coef"]), T)
+    assert np.array_equal(dec, np.asarray(enc["recon"]))
+    ddev = torch.empty((ce.num_p_frames(T), H, W, 3), dtype=torch.uint8, device="cuda")
+    cd.decode_device(torch.from_numpy(refs).cuda(), enc["mv"].cuda(), enc["coef"].cuda(), ddev, T)
+    torch.cuda.synchronize()
+    assert np.array_equal(ddev.cpu().numpy(), dec)
+    prm = orc.symmetric_search_params(R)
+    for p, t in enumerate(ce.p_frame_indices(T)):
+        o = orc.encode_p(clip[t], clip[(t // g) * g], bs, round_mode=int(coef_mode != 0), **prm)
+        assert np.array_equal(dec[p], o["recon"])
+
+
+@pytest.mark.parametrize("qf", [10, 50, 99])
+def test_sparsity_on_device(vcs, golden, golden_meta, qf):
+    """The sparsity print of DCTCompression/dct.py:188-191 from a device reduction."""
+    import torch
+    from vcs_h264_b200.DCTcompressor import quality_tables
+    img = golden["still_img"]
+    dc = vcs.DCTCompressor(8)
+    dc.Q = quality_tables(qf)
+    idx = torch.from_numpy(dc.compress_indices(img)).cuda()
+    ctx = vcs.runtime.get_context()
+    assert vcs.sparsity_device(ctx, idx, vcs.COEF_I16_RINT) == golden_meta[f"still_q{qf}_sparsity"]
+    pl = torch.from_numpy(np.stack(dc.compress(img, rounded=True))).cuda()
+    assert vcs.sparsity_device(ctx, pl, vcs.COEF_F64_RINT) == golden_meta[f"still_q{qf}_sparsity"]

@@ -11,7 +11,7 @@ from .motion import MotionProcessor
 from .DCTcompressor import DCTCompressor
 from .encoder import Encoder
 from .decoder import Decoder
-from .clip import ClipEncoder
+from .clip import ClipDecoder, ClipEncoder, sparsity_device
 
-__all__ = ["MotionProcessor", "DCTCompressor", "Encoder", "Decoder", "Frame", "ClipEncoder",
+__all__ = ["MotionProcessor", "DCTCompressor", "Encoder", "Decoder", "Frame", "ClipEncoder", "ClipDecoder", "sparsity_device",
            "VcsError", "_capi"]

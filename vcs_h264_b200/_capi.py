@@ -76,6 +76,9 @@ SIGNATURES = {
     "vcs_residual_dct_clip_dev": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "vcs_encode_clip_dev": (_i, [_vp, _PP, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "vcs_encode_clip_host": (_i, [_vp, _PP, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vcs_decode_clip_dev": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
+    "vcs_decode_clip_host": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
+    "vcs_count_nonzero_dev": (_i, [_vp, _i, _vp, _sz, C.POINTER(C.c_ulonglong)]),
     "vcs_microbench": (_i, [_vp, _i, _i, C.POINTER(_d), C.POINTER(_d)]),
     "vcs_enable_kernel_timing": (_i, [_vp, _i]),
     "vcs_kernel_times": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i)]),

@@ -122,3 +122,44 @@ class ClipEncoder:
         self.ctx.call("vcs_me_search_clip_dev", self.params, _capi.ptr(frames_dev), T, self.gop_len,
                       _capi.ptr(out["mv"]), _capi.ptr(out.get("cost")), _capi.ptr(out.get("flags")))
         return out
+
+
+class ClipDecoder:
+    """Decoder.reconstruct_video's per-frame arithmetic (decoder.py:23-69) for a whole clip: motion
+    compensation from the ORIGINAL I-frames, dequantise, IDCT, truncating store, YCrCb->BGR, wrap add."""
+
+    def __init__(self, shape, block_size=16, gop_len=4, qf=50.0, coef_mode=_capi.COEF_I16_RINT, device=0):
+        self.H, self.W, self.bs, self.gop_len = int(shape[0]), int(shape[1]), block_size, gop_len
+        self.coef_mode, self.device = coef_mode, device
+        self.ctx = get_context(device)
+        self.Q = _capi.q_tables(qf)
+
+    def decode_host(self, ref_frames, mv, coef, T):
+        """ref_frames uint8 [nG,H,W,3] (the I-frames), mv int16 [nP,N,2], coef [nP,3,H,W] -> uint8 [nP,H,W,3]."""
+        nP = _capi.num_p_frames(T, self.gop_len)
+        mv = np.ascontiguousarray(np.asarray(mv), np.int16)
+        coef = np.ascontiguousarray(np.asarray(coef), COEF_DTYPES[self.coef_mode])
+        ref_frames = np.ascontiguousarray(np.asarray(ref_frames), np.uint8)
+        out = np.empty((nP, self.H, self.W, 3), np.uint8)
+        self.ctx.set_q(self.Q)
+        self.ctx.call("vcs_decode_clip_host", self.H, self.W, self.bs, ref_frames.ctypes.data, T, self.gop_len,
+                      mv.ctypes.data, self.coef_mode, coef.ctypes.data, out.ctypes.data)
+        return out
+
+    def decode_device(self, ref_frames_dev, mv_dev, coef_dev, recon_dev, T, stream=None):
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream(recon_dev.device)
+        self.ctx.set_stream(s.cuda_stream)
+        self.ctx.set_q(self.Q)
+        self.ctx.call("vcs_decode_clip_dev", self.H, self.W, self.bs, _capi.ptr(ref_frames_dev), T, self.gop_len,
+                      _capi.ptr(mv_dev), self.coef_mode, _capi.ptr(coef_dev), _capi.ptr(recon_dev))
+        return recon_dev
+
+
+def sparsity_device(ctx, coef_dev, coef_mode):
+    """1 - nnz/size of a device coefficient tensor (the print of DCTCompression/dct.py:188-191)."""
+    import ctypes as C
+    cnt = C.c_ulonglong(0)
+    n = coef_dev.numel()
+    ctx.call("vcs_count_nonzero_dev", coef_mode, _capi.ptr(coef_dev), n, C.byref(cnt))
+    return 1.0 - cnt.value / float(n)

@@ -141,32 +141,35 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
         if (g_on) {
             const int x = x0 + g_c, y = y0 + g_r;
             uint32_t pw[6] = {0, 0, 0, 0, 0, 0};
+            // prediction: motion-compensated gather from ref (motion.py:42-69) or a given pred image
+            if (mv && ref) {
+                if (bs % 8 == 0) {   // the group lies inside one macroblock
+                    const int mbx = x / bs, mby = y / bs;
+                    if (mbx < nbx && mby < nby) {   // uncovered border stays 0 (motion.py:45-46)
+                        const int16_t *m = mv + 2 * (mby * nbx + mbx);
+                        load24(ref + ((size_t)(y + m[1]) * W + (x + m[0])) * 3, pw);
+                    }
+                } else {             // per-pixel gather (block sizes that are not multiples of 8)
+                    for (int u = 0; u < 8; ++u) {
+                        const int mbx = (x + u) / bs, mby = y / bs;
+                        uint32_t b3 = 0;
+                        if (mbx < nbx && mby < nby) {
+                            const int16_t *m = mv + 2 * (mby * nbx + mbx);
+                            const uint8_t *rp = ref + ((size_t)(y + m[1]) * W + (x + u + m[0])) * 3;
+                            b3 = (uint32_t)__ldg(rp) | ((uint32_t)__ldg(rp + 1) << 8) | ((uint32_t)__ldg(rp + 2) << 16);
+                        }
+                        for (int e = 0; e < 3; ++e) s_pred[(g_r * DCT_TILE_W + g_c + u) * 3 + e] = (uint8_t)(b3 >> (8 * e));
+                    }
+                    const uint32_t *sp = reinterpret_cast<const uint32_t *>(s_pred + (g_r * DCT_TILE_W + g_c) * 3);
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) pw[k] = sp[k];
+                }
+            } else if (a.pred_in) {
+                load24(a.pred_in + (size_t)p * npix * 3 + ((size_t)y * W + x) * 3, pw);
+            }
             if (forward) {
                 uint32_t cw[6];
                 load24(cur + ((size_t)y * W + x) * 3, cw);
-                if (mv) {
-                    if (bs % 8 == 0) {   // the group lies inside one macroblock
-                        const int mbx = x / bs, mby = y / bs;
-                        if (mbx < nbx && mby < nby) {   // uncovered border stays 0 (motion.py:45-46)
-                            const int16_t *m = mv + 2 * (mby * nbx + mbx);
-                            load24(ref + ((size_t)(y + m[1]) * W + (x + m[0])) * 3, pw);
-                        }
-                    } else {             // per-pixel gather (block sizes that are not multiples of 8)
-                        for (int u = 0; u < 8; ++u) {
-                            const int mbx = (x + u) / bs, mby = y / bs;
-                            uint32_t b3 = 0;
-                            if (mbx < nbx && mby < nby) {
-                                const int16_t *m = mv + 2 * (mby * nbx + mbx);
-                                const uint8_t *rp = ref + ((size_t)(y + m[1]) * W + (x + u + m[0])) * 3;
-                                b3 = (uint32_t)__ldg(rp) | ((uint32_t)__ldg(rp + 1) << 8) | ((uint32_t)__ldg(rp + 2) << 16);
-                            }
-                            for (int e = 0; e < 3; ++e) s_pred[(g_r * DCT_TILE_W + g_c + u) * 3 + e] = (uint8_t)(b3 >> (8 * e));
-                        }
-                        const uint32_t *sp = reinterpret_cast<const uint32_t *>(s_pred + (g_r * DCT_TILE_W + g_c) * 3);
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) pw[k] = sp[k];
-                    }
-                }
                 // residual wraps mod 256 per byte (motion.py:39) and is then treated as a BGR image
                 uint32_t rw[6];
 #pragma unroll
@@ -184,8 +187,6 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                 *reinterpret_cast<uint2 *>(s_in8 + (0 * 8 + g_r) * DCT_TILE_W + g_c) = make_uint2(yv[0], yv[1]);
                 *reinterpret_cast<uint2 *>(s_in8 + (1 * 8 + g_r) * DCT_TILE_W + g_c) = make_uint2(crv[0], crv[1]);
                 *reinterpret_cast<uint2 *>(s_in8 + (2 * 8 + g_r) * DCT_TILE_W + g_c) = make_uint2(cbv[0], cbv[1]);
-            } else if (a.pred_in) {
-                load24(a.pred_in + (size_t)p * npix * 3 + ((size_t)y * W + x) * 3, pw);
             }
             uint32_t *sp = reinterpret_cast<uint32_t *>(s_pred + (g_r * DCT_TILE_W + g_c) * 3);
 #pragma unroll
@@ -395,6 +396,20 @@ __global__ void mc_kernel(const uint8_t *__restrict__ ref, const int16_t *__rest
         }
         pred[3 * k] = b; pred[3 * k + 1] = g; pred[3 * k + 2] = r;
     }
+}
+
+// Non-zero count of quantised coefficients: the numerator of DCTCompression/dct.py:188-191's sparsity
+// print (1 - nnz/size).  ELEM: 2 = int16 planes, 8 = float64 planes.
+template <int ELEM>
+__global__ void count_nonzero_kernel(const void *__restrict__ coef, size_t n, unsigned long long *__restrict__ out) {
+    unsigned long long c = 0;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        if (ELEM == 2) c += reinterpret_cast<const int16_t *>(coef)[k] != 0;
+        else c += reinterpret_cast<const double *>(coef)[k] != 0.0;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) c += shfl_xor_u64(c, m);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // get_residuals (motion.py:38-40) / _fully_reconstruct (decoder.py:57): byte-wise wrap

@@ -598,6 +598,75 @@ int vcs_residual_dct_clip_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t 
     return launch_dct(ctx, ctx->stream, a, vcs_num_p_frames(T, gop_len));
 }
 
+// Decoder._reconstruct_P_frame over a clip (decoder.py:52-69): MC from the ORIGINAL I-frames + dequantise +
+// IDCT + truncating store + YCrCb->BGR + wrap add, one launch.
+int vcs_decode_clip_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_frames, int T, int gop_len,
+                        const int16_t *mv, int coef_mode, const void *coef, uint8_t *recon) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!ref_frames || !mv || !coef || !recon || gop_len < 2 || T < 1 || bs <= 0 || H < bs || W < bs)
+        return fail(ctx, VCS_E_INVALID, "bad decode arguments");
+    const long long fs = (long long)H * W * 3;
+    DctArgs a;
+    memset(&a, 0, sizeof(a));
+    a.H = H; a.W = W; a.has_fa = 1; a.mv = mv; a.bs = bs; a.nbx = W / bs; a.nby = H / bs;
+    a.fa.cur_base = ref_frames; a.fa.ref_base = ref_frames;      // only the I-frames are given: [nG][H][W][3]
+    a.fa.cur_gop_stride = fs; a.fa.cur_frame_stride = 0; a.fa.ref_gop_stride = fs; a.fa.ppg = gop_len - 1;
+    a.forward = 0; a.inverse = 1; a.coef_mode = coef_mode; a.coef = const_cast<void *>(coef); a.recon = recon;
+    return launch_dct(ctx, ctx->stream, a, vcs_num_p_frames(T, gop_len));
+}
+
+int vcs_decode_clip_host(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_frames, int T, int gop_len,
+                         const int16_t *mv, int coef_mode, const void *coef, uint8_t *recon) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!ref_frames || !mv || !coef || !recon || gop_len < 2 || T < 1 || bs <= 0 || H < bs || W < bs)
+        return fail(ctx, VCS_E_INVALID, "bad decode arguments");
+    if (H % 8 || W % 8 || coef_mode < 0 || coef_mode > 2)
+        return fail(ctx, VCS_E_INVALID, "H=%d W=%d must be multiples of 8; coef_mode=%d", H, W, coef_mode);
+    const size_t fs = (size_t)H * W * 3, npix = (size_t)H * W, ce = coef_elem(coef_mode);
+    const int N = vcs_num_blocks(H, W, bs), nP = vcs_num_p_frames(T, gop_len), nG = (T + gop_len - 1) / gop_len;
+    // the reference would fail on a vector pointing outside the frame (motion.py:62-65)
+    for (long long k = 0; k < (long long)nP * N; ++k) {
+        const int b = (int)(k % N);
+        const int x = (b % (W / bs)) * bs + mv[2 * k], y = (b / (W / bs)) * bs + mv[2 * k + 1];
+        if (x < 0 || y < 0 || x + bs > W || y + bs > H)
+            return fail(ctx, VCS_E_INVALID, "motion vector %lld points outside the frame", k);
+    }
+    uint8_t *d_ref, *d_rec; int16_t *d_mv; void *d_coef; int rc;
+    if ((rc = dev_buf(ctx, S_FRAMES, fs * nG, (void **)&d_ref))) return rc;
+    if ((rc = dev_buf(ctx, S_MV, (size_t)nP * N * 4 + 4, (void **)&d_mv))) return rc;
+    if ((rc = dev_buf(ctx, S_COEF, (size_t)nP * npix * 3 * ce + 8, &d_coef))) return rc;
+    if ((rc = dev_buf(ctx, S_RECON, (size_t)nP * fs + 4, (void **)&d_rec))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(d_ref, ref_frames, fs * nG, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(d_mv, mv, (size_t)nP * N * 4, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(d_coef, coef, (size_t)nP * npix * 3 * ce, cudaMemcpyHostToDevice, st));
+    if ((rc = vcs_decode_clip_dev(ctx, H, W, bs, d_ref, T, gop_len, d_mv, coef_mode, d_coef, d_rec))) return rc;
+    CK(ctx, cudaMemcpyAsync(recon, d_rec, (size_t)nP * fs, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return VCS_OK;
+}
+
+// numerator of dct.py:188-191's sparsity: number of non-zero coefficients in n elements (device pointer)
+int vcs_count_nonzero_dev(vcs_ctx *ctx, int coef_mode, const void *coef, size_t n, unsigned long long *count_host) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!coef || !count_host || coef_mode < 0 || coef_mode > 2) return fail(ctx, VCS_E_INVALID, "bad arguments");
+    unsigned long long *d_cnt; int rc;
+    if ((rc = dev_buf(ctx, S_CYC, 8, (void **)&d_cnt))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemsetAsync(d_cnt, 0, 8, st));
+    if (n) {
+        int blocks = (int)((n + 1023) / 1024);
+        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        if (coef_mode == VCS_COEF_I16_RINT) count_nonzero_kernel<2><<<blocks, 256, 0, st>>>(coef, n, d_cnt);
+        else count_nonzero_kernel<8><<<blocks, 256, 0, st>>>(coef, n, d_cnt);
+        CK(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    CK(ctx, cudaMemcpyAsync(count_host, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return VCS_OK;
+}
+
 int vcs_encode_clip_dev(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
                         int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef,
                         uint8_t *recon) {

@@ -181,6 +181,24 @@ int vcs_decode_clip_host(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_
 int vcs_count_nonzero_dev(vcs_ctx *ctx, int coef_mode, const void *coef, size_t n,
                           unsigned long long *count_host);
 
+/* ---- intra mode decision: IntraframeCompression/intraframe.py + intramodes.py --------- */
+/* luma4x4 (intraframe.py:24-151): 9 predictors per 4x4 block, first strict SAD minimum, neighbours from the
+ * ORIGINAL plane.  Y: uint8 H x W (multiples of 4); res / pred: int32 H x W; modes: uint8 (H/4) x (W/4). */
+int vcs_intra_luma4x4_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, int32_t *res, int32_t *pred,
+                          uint8_t *modes);
+/* luma16x16 (intraframe.py:153-225): vertical / horizontal / dc per 16x16 block. */
+int vcs_intra_luma16x16_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, int32_t *res, int32_t *pred,
+                            uint8_t *modes);
+/* chroma8x8 (intraframe.py:228-317): joint mode for Cr and Cb per 8x8 block; Cb's upper neighbour is the
+ * residual row above (intraframe.py:266), so residuals / predictions are int32. */
+int vcs_intra_chroma8x8_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Cr, const uint8_t *Cb,
+                            int32_t *crres, int32_t *crpred, int32_t *cbres, int32_t *cbpred,
+                            uint8_t *modes);
+/* the three above from host buffers: which = 0 luma4x4, 1 luma16x16 (p0 = Y; p1, res1, pred1 unused),
+ * 2 chroma8x8 (p0 = Cr, p1 = Cb; res0/pred0 = Cr outputs, res1/pred1 = Cb outputs) */
+int vcs_intra_host(vcs_ctx *ctx, int which, int H, int W, const uint8_t *p0, const uint8_t *p1,
+                   int32_t *res0, int32_t *pred0, int32_t *res1, int32_t *pred1, uint8_t *modes);
+
 /* ---- measurement support ------------------------------------------------------------------ */
 /* Register-only issue-rate microbenchmarks that define the INT32-pipe roofline on the box the
  * bench runs on.  which: 0 VABSDIFF4.U8.ACC, 1 IADD3, 2 LOP3, 3 IMAD, 4 IDP.4A,

@@ -224,3 +224,44 @@ def max_threads():
 
 def selfcheck_simd():
     return lib().vcs_oracle_selfcheck_simd()
+
+
+def _plane(a):
+    a = np.ascontiguousarray(a)
+    assert a.dtype == np.uint8 and a.ndim == 2
+    return a
+
+
+def luma4x4(Y):
+    """luma4x4 (IntraframeCompression/intraframe.py:24-151) -> (res int32, pred int32, modes uint8)."""
+    Y = _plane(Y)
+    H, W = Y.shape
+    res = np.empty((H, W), np.int32); pred = np.empty((H, W), np.int32); modes = np.empty((H // 4, W // 4), np.uint8)
+    rc = lib().vcs_oracle_luma4x4(_p(Y, C.c_uint8), H, W, _p(res, C.c_int32), _p(pred, C.c_int32), _p(modes, C.c_uint8))
+    if rc:
+        raise ValueError("luma4x4 needs sides that are multiples of 4")
+    return res, pred, modes
+
+
+def luma16x16(Y):
+    """luma16x16 (intraframe.py:153-225)."""
+    Y = _plane(Y)
+    H, W = Y.shape
+    res = np.empty((H, W), np.int32); pred = np.empty((H, W), np.int32); modes = np.empty((H // 16, W // 16), np.uint8)
+    rc = lib().vcs_oracle_luma16x16(_p(Y, C.c_uint8), H, W, _p(res, C.c_int32), _p(pred, C.c_int32), _p(modes, C.c_uint8))
+    if rc:
+        raise ValueError("luma16x16 needs sides that are multiples of 16")
+    return res, pred, modes
+
+
+def chroma8x8(Cr, Cb):
+    """chroma8x8 (intraframe.py:228-317) -> (Crres, Crpred, Cbres, Cbpred int32, modes uint8)."""
+    Cr, Cb = _plane(Cr), _plane(Cb)
+    H, W = Cr.shape
+    outs = [np.empty((H, W), np.int32) for _ in range(4)]
+    modes = np.empty((H // 8, W // 8), np.uint8)
+    rc = lib().vcs_oracle_chroma8x8(_p(Cr, C.c_uint8), _p(Cb, C.c_uint8), H, W, *[_p(o, C.c_int32) for o in outs],
+                                    _p(modes, C.c_uint8))
+    if rc:
+        raise ValueError("chroma8x8 needs sides that are multiples of 8")
+    return (*outs, modes)

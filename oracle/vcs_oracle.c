@@ -475,3 +475,230 @@ int vcs_oracle_max_threads(void) {
     return 1;
 #endif
 }
+
+/* ==================================================================================== */
+/* Intra mode decision: IntraframeCompression/intraframe.py + intramodes.py */
+/* ==================================================================================== */
+/* All predictor values are integers (the reference computes them with // in uint8 or float64
+ * arithmetic), so the restatement works in int.  The reference's type quirks are reproduced:
+ *  - 3*x//4 wraps mod 256 before the division when x is a uint8 pixel (a real neighbour slice),
+ *    not when it is the float fallback 128 or a replicated value (intramodes.py:42,135);
+ *  - dc4x4 adds u+l element-wise in uint8 (wrap) only when BOTH are real neighbours (intramodes.py:21);
+ *  - neighbours are ORIGINAL pixels (intraframe.py:58-77), availability follows the aliased
+ *    `available` list: first row: left only; first column: up (+up-right for 4x4); last 4x4
+ *    column: no up-right (replicated u[3]); otherwise everything (intraframe.py:38-55);
+ *  - chroma: the Cb UP neighbour is the RESIDUAL row above (Cbres, intraframe.py:266), which makes
+ *    block rows of one column depend on each other; residuals/predictions can leave [0,255];
+ *  - first strict minimum over the modes, initial best = bs*bs*255 (x2 for chroma) with an
+ *    all-zero prediction and mode 0 if nothing beats it (intraframe.py:79-81).                  */
+
+static inline int fdiv(int a, int b) { /* Python floor division, b > 0 */
+    int q = a / b;
+    return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+
+/* one 4x4 predictor set; u8flags: bit0 u is uint8, bit1 ur is uint8, bit2 l is uint8 (for the wraps) */
+static void pred4x4(int mode, int ul, const int *u, const int *ur, const int *l, int u_u8, int ur_u8, int l_u8,
+                    int P[16]) {
+#define Q4(x) fdiv((x), 4)
+#define H2(x) fdiv((x), 2)
+    const int t3ur = ur_u8 ? ((3 * ur[3]) & 255) / 4 : fdiv(3 * ur[3], 4);
+    const int t3l = l_u8 ? ((3 * l[3]) & 255) / 4 : fdiv(3 * l[3], 4);
+    switch (mode) {
+    case 0: for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) P[i * 4 + j] = u[j]; break;
+    case 1: for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) P[i * 4 + j] = l[i]; break; /* pred[:,c] = l (intramodes.py:16) */
+    case 2: {
+        int s = 0;
+        for (int k = 0; k < 4; ++k) s += (u_u8 && l_u8) ? ((u[k] + l[k]) & 255) : (u[k] + l[k]);
+        int avg = fdiv(s, 8);
+        for (int k = 0; k < 16; ++k) P[k] = avg;
+        break;
+    }
+    case 3: /* downleft4x4 (intramodes.py:26-44) */
+        P[0] = Q4(u[0]) + H2(u[1]) + Q4(u[2]);
+        P[1] = Q4(u[1]) + H2(u[2]) + Q4(u[3]); P[4] = P[1];
+        P[2] = Q4(u[2]) + H2(u[3]) + Q4(ur[0]); P[5] = P[2]; P[8] = P[2];
+        P[3] = Q4(u[3]) + H2(ur[0]) + Q4(ur[1]); P[6] = P[3]; P[9] = P[3]; P[12] = P[3];
+        P[7] = Q4(ur[0]) + H2(ur[1]) + Q4(ur[2]); P[10] = P[7]; P[13] = P[7];
+        P[11] = Q4(ur[1]) + H2(ur[2]) + Q4(ur[3]); P[14] = P[11];
+        P[15] = Q4(ur[2]) + t3ur;
+        break;
+    case 4: /* downright4x4 (intramodes.py:46-64) */
+        P[3] = Q4(u[1]) + H2(u[2]) + Q4(u[3]);
+        P[2] = Q4(u[0]) + H2(u[1]) + Q4(u[2]); P[7] = P[2];
+        P[1] = Q4(ul) + H2(u[0]) + Q4(u[1]); P[6] = P[1]; P[11] = P[1];
+        P[0] = Q4(ul) + H2(u[0]) + Q4(l[0]); P[5] = P[0]; P[10] = P[0]; P[15] = P[0];
+        P[4] = Q4(u[0]) + H2(l[0]) + Q4(l[1]); P[9] = P[4]; P[14] = P[4];
+        P[8] = Q4(l[0]) + H2(l[1]) + Q4(l[2]); P[13] = P[8];
+        P[12] = Q4(l[1]) + H2(l[2]) + Q4(l[3]);
+        break;
+    case 5: /* verticalright4x4 (intramodes.py:66-84) */
+        P[0] = H2(ul) + H2(u[0]); P[9] = P[0];
+        P[1] = H2(u[0]) + H2(u[1]); P[10] = P[1];
+        P[2] = H2(u[1]) + H2(u[2]); P[11] = P[2];
+        P[3] = H2(u[2]) + H2(u[3]);
+        P[4] = Q4(u[0]) + H2(ul) + Q4(l[0]); P[13] = P[4];
+        P[5] = Q4(ul) + H2(u[0]) + Q4(u[1]); P[14] = P[5];
+        P[6] = Q4(u[0]) + H2(u[1]) + Q4(u[2]); P[15] = P[6];
+        P[7] = Q4(u[1]) + H2(u[2]) + Q4(u[3]);
+        P[8] = Q4(ul) + H2(l[0]) + Q4(l[1]);
+        P[12] = Q4(l[0]) + H2(l[1]) + Q4(l[2]);
+        break;
+    case 6: /* horizontaldown4x4 (intramodes.py:86-104) */
+        P[0] = H2(ul) + H2(l[0]); P[6] = P[0];
+        P[1] = Q4(u[0]) + H2(ul) + Q4(l[0]); P[7] = P[1];
+        P[2] = Q4(ul) + H2(u[0]) + Q4(u[1]);
+        P[3] = Q4(u[0]) + H2(u[1]) + Q4(u[2]);
+        P[4] = H2(l[0]) + H2(l[1]); P[10] = P[4];
+        P[5] = Q4(ul) + H2(l[1]) + Q4(l[2]); P[11] = P[5];
+        P[8] = H2(l[1]) + H2(l[2]); P[14] = P[8];
+        P[9] = Q4(l[0]) + H2(l[1]) + Q4(l[2]); P[15] = P[9];
+        P[12] = H2(l[2]) + H2(l[3]);
+        P[13] = Q4(l[1]) + H2(l[2]) + Q4(l[3]);
+        break;
+    case 7: /* verticalleft4x4 (intramodes.py:106-124) */
+        P[0] = H2(u[0]) + H2(u[1]);
+        P[1] = H2(u[1]) + H2(u[2]); P[8] = P[1];
+        P[2] = H2(u[2]) + H2(u[3]); P[9] = P[2];
+        P[3] = H2(u[3]) + H2(ur[0]); P[10] = P[3];
+        P[11] = H2(ur[0]) + H2(ur[1]);
+        P[4] = Q4(u[0]) + H2(u[1]) + Q4(u[2]);
+        P[5] = Q4(u[1]) + H2(u[2]) + Q4(u[3]); P[12] = P[5];
+        P[6] = Q4(u[2]) + H2(u[3]) + Q4(ur[0]); P[13] = P[6];
+        P[7] = Q4(u[3]) + H2(ur[0]) + Q4(ur[1]); P[14] = P[7];
+        P[15] = Q4(ur[0]) + H2(ur[1]) + Q4(ur[2]);
+        break;
+    default: /* 8: horizontalup4x4 (intramodes.py:126-143) */
+        P[0] = H2(l[0]) + H2(l[1]);
+        P[1] = Q4(l[0]) + H2(l[1]) + Q4(l[2]);
+        P[2] = H2(l[1]) + H2(l[2]); P[4] = P[2];
+        P[3] = Q4(l[1]) + H2(l[2]) + Q4(l[3]); P[5] = P[3];
+        P[6] = H2(l[2]) + H2(l[3]); P[8] = P[6];
+        P[7] = Q4(l[2]) + t3l; P[9] = P[7];
+        P[12] = l[3]; P[10] = l[3]; P[11] = l[3]; P[13] = l[3]; P[14] = l[3]; P[15] = l[3];
+        break;
+    }
+#undef Q4
+#undef H2
+}
+
+/* luma4x4 (IntraframeCompression/intraframe.py:24-151).  Y: H x W uint8 (multiples of 4).
+ * res, pred: H x W int32; modes: (H/4) x (W/4) uint8. */
+int vcs_oracle_luma4x4(const uint8_t *Y, int H, int W, int32_t *res, int32_t *pred, uint8_t *modes) {
+    if (H % 4 || W % 4 || H <= 0 || W <= 0) return -1;
+    const int mr = H / 4, mc = W / 4;
+    for (int im = 0; im < mr; ++im)
+        for (int jm = 0; jm < mc; ++jm) {
+            const int i = im * 4, j = jm * 4;
+            int s_ul = 0, s_u = 0, s_ur = 0, s_l = 0;
+            if (im == 0 && jm == 0) { }
+            else if (im == 0) s_l = 1;
+            else if (jm == 0) { s_u = 1; s_ur = 1; }
+            else if (jm + 1 == mc) { s_ul = 1; s_u = 1; s_l = 1; }
+            else { s_ul = s_u = s_ur = s_l = 1; }
+            if (mc == 1 && im > 0) s_ur = 0;  /* single column: available[...][jMac+1] raises IndexError in the
+                                                 reference; a one-block-wide plane is outside its domain */
+            int ul = s_ul ? Y[(i - 1) * W + j - 1] : 128, u[4], ur[4], l[4];
+            for (int k = 0; k < 4; ++k) {
+                u[k] = s_u ? Y[(i - 1) * W + j + k] : 128;
+                ur[k] = s_ur ? Y[(i - 1) * W + j + 4 + k] : (s_u ? Y[(i - 1) * W + j + 3] : 128);
+                l[k] = s_l ? Y[(i + k) * W + j - 1] : 128;
+            }
+            int best = 16 * 255, bmode = 0, bp[16] = {0};
+            for (int m = 0; m < 9; ++m) {
+                int P[16];
+                pred4x4(m, ul, u, ur, l, s_u, s_ur, s_l, P);
+                int d = 0;
+                for (int a = 0; a < 4; ++a)
+                    for (int b = 0; b < 4; ++b) d += abs(P[a * 4 + b] - (int)Y[(i + a) * W + j + b]);
+                if (d < best) { best = d; bmode = m; memcpy(bp, P, sizeof(bp)); }
+            }
+            for (int a = 0; a < 4; ++a)
+                for (int b = 0; b < 4; ++b) {
+                    pred[(i + a) * W + j + b] = bp[a * 4 + b];
+                    res[(i + a) * W + j + b] = (int)Y[(i + a) * W + j + b] - bp[a * 4 + b];
+                }
+            modes[im * mc + jm] = (uint8_t)bmode;
+        }
+    return 0;
+}
+
+/* luma16x16 (intraframe.py:153-225): vertical / horizontal / dc16x16 (intramodes.py:145-161). */
+int vcs_oracle_luma16x16(const uint8_t *Y, int H, int W, int32_t *res, int32_t *pred, uint8_t *modes) {
+    if (H % 16 || W % 16 || H <= 0 || W <= 0) return -1;
+    const int mr = H / 16, mc = W / 16;
+    for (int im = 0; im < mr; ++im)
+        for (int jm = 0; jm < mc; ++jm) {
+            const int i = im * 16, j = jm * 16;
+            const int s_u = im > 0, s_l = jm > 0;   /* ul is fetched but never used by the three modes */
+            int u[16], l[16];
+            long su = 0, sl = 0;
+            for (int k = 0; k < 16; ++k) {
+                u[k] = s_u ? Y[(i - 1) * W + j + k] : 128;
+                l[k] = s_l ? Y[(i + k) * W + j - 1] : 128;
+                su += u[k]; sl += l[k];
+            }
+            const int dc = fdiv((int)(su + sl), 32);
+            long best = 16 * 16 * 255; int bmode = 0, any = 0;
+            for (int m = 0; m < 3; ++m) {
+                long d = 0;
+                for (int a = 0; a < 16; ++a)
+                    for (int b = 0; b < 16; ++b) {
+                        int pv = m == 0 ? u[b] : (m == 1 ? l[a] : dc);   /* horizontal16x16: pred[:,c] = l */
+                        d += labs((long)pv - (long)Y[(i + a) * W + j + b]);
+                    }
+                if (d < best) { best = d; bmode = m; any = 1; }
+            }
+            for (int a = 0; a < 16; ++a)
+                for (int b = 0; b < 16; ++b) {
+                    int pv = !any ? 0 : (bmode == 0 ? u[b] : (bmode == 1 ? l[a] : dc));
+                    pred[(i + a) * W + j + b] = pv;
+                    res[(i + a) * W + j + b] = (int)Y[(i + a) * W + j + b] - pv;
+                }
+            modes[im * mc + jm] = (uint8_t)bmode;
+        }
+    return 0;
+}
+
+/* chroma8x8 (intraframe.py:228-317): joint mode for Cr and Cb; Cb's up neighbour is the RESIDUAL row
+ * above (Cbres, intraframe.py:266). */
+int vcs_oracle_chroma8x8(const uint8_t *Cr, const uint8_t *Cb, int H, int W, int32_t *crres, int32_t *crpred,
+                         int32_t *cbres, int32_t *cbpred, uint8_t *modes) {
+    if (H % 8 || W % 8 || H <= 0 || W <= 0) return -1;
+    const int mr = H / 8, mc = W / 8;
+    for (int im = 0; im < mr; ++im)
+        for (int jm = 0; jm < mc; ++jm) {
+            const int i = im * 8, j = jm * 8;
+            const int s_u = im > 0, s_l = jm > 0;
+            int ur[8], ub[8], lr[8], lb[8];
+            long sur = 0, sub = 0, slr = 0, slb = 0;
+            for (int k = 0; k < 8; ++k) {
+                ur[k] = s_u ? Cr[(i - 1) * W + j + k] : 128;
+                ub[k] = s_u ? cbres[(i - 1) * W + j + k] : 128;
+                lr[k] = s_l ? Cr[(i + k) * W + j - 1] : 128;
+                lb[k] = s_l ? Cb[(i + k) * W + j - 1] : 128;
+                sur += ur[k]; sub += ub[k]; slr += lr[k]; slb += lb[k];
+            }
+            const int dcr = fdiv((int)(sur + slr), 16), dcb = fdiv((int)(sub + slb), 16);
+            long best = 2 * 8 * 8 * 255; int bmode = 0, any = 0;
+            for (int m = 0; m < 3; ++m) {
+                long d = 0;
+                for (int a = 0; a < 8; ++a)
+                    for (int b = 0; b < 8; ++b) {
+                        int pr = m == 0 ? ur[b] : (m == 1 ? lr[a] : dcr);
+                        int pb = m == 0 ? ub[b] : (m == 1 ? lb[a] : dcb);
+                        d += labs((long)pr - (long)Cr[(i + a) * W + j + b]) + labs((long)pb - (long)Cb[(i + a) * W + j + b]);
+                    }
+                if (d < best) { best = d; bmode = m; any = 1; }
+            }
+            for (int a = 0; a < 8; ++a)
+                for (int b = 0; b < 8; ++b) {
+                    int pr = !any ? 0 : (bmode == 0 ? ur[b] : (bmode == 1 ? lr[a] : dcr));
+                    int pb = !any ? 0 : (bmode == 0 ? ub[b] : (bmode == 1 ? lb[a] : dcb));
+                    crpred[(i + a) * W + j + b] = pr; crres[(i + a) * W + j + b] = (int)Cr[(i + a) * W + j + b] - pr;
+                    cbpred[(i + a) * W + j + b] = pb; cbres[(i + a) * W + j + b] = (int)Cb[(i + a) * W + j + b] - pb;
+                }
+            modes[im * mc + jm] = (uint8_t)bmode;
+        }
+    return 0;
+}

@@ -14,6 +14,7 @@
 #include "../../include/vcs_b200.h"
 #include "common.cuh"
 #include "dct_stage.cuh"
+#include "intra.cuh"
 #include "me_generic.cuh"
 #include "me_tiled.cuh"
 #include "microbench.cuh"
@@ -743,6 +744,85 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
     }
     CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
     CK(ctx, cudaStreamSynchronize(sc));
+    return VCS_OK;
+}
+
+// ---- intra mode decision (IntraframeCompression/intraframe.py:24-317) ---------------------------
+static int intra_check(vcs_ctx *ctx, int H, int W, int m, const void *a, const void *b) {
+    if (!a || !b) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    if (H <= 0 || W <= 0 || H % m || W % m)
+        return fail(ctx, VCS_E_INVALID, "plane sides must be positive multiples of %d", m);
+    return VCS_OK;
+}
+
+int vcs_intra_luma4x4_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, int32_t *res, int32_t *pred, uint8_t *modes) {
+    if (!ctx) return VCS_E_INVALID;
+    int rc = intra_check(ctx, H, W, 4, Y, modes);
+    if (rc) return rc;
+    if (!res || !pred || (W / 4 < 2 && H / 4 > 1))
+        return fail(ctx, VCS_E_INVALID, "luma4x4 needs at least two block columns (the reference indexes column j+1)");
+    const int nb = (H / 4) * (W / 4);
+    intra_luma4x4_kernel<<<(nb + 127) / 128, 128, 0, ctx->stream>>>(Y, H, W, res, pred, modes);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return VCS_OK;
+}
+
+int vcs_intra_luma16x16_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, int32_t *res, int32_t *pred, uint8_t *modes) {
+    if (!ctx) return VCS_E_INVALID;
+    int rc = intra_check(ctx, H, W, 16, Y, modes);
+    if (rc) return rc;
+    if (!res || !pred) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    const int nb = (H / 16) * (W / 16);
+    intra_luma16x16_kernel<<<(nb * 32 + 255) / 256, 256, 0, ctx->stream>>>(Y, H, W, res, pred, modes);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return VCS_OK;
+}
+
+int vcs_intra_chroma8x8_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Cr, const uint8_t *Cb, int32_t *crres,
+                            int32_t *crpred, int32_t *cbres, int32_t *cbpred, uint8_t *modes) {
+    if (!ctx) return VCS_E_INVALID;
+    int rc = intra_check(ctx, H, W, 8, Cr, Cb);
+    if (rc) return rc;
+    if (!crres || !crpred || !cbres || !cbpred || !modes) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    const int ncol = W / 8;
+    intra_chroma8x8_kernel<<<(ncol * 32 + 127) / 128, 128, 0, ctx->stream>>>(Cr, Cb, H, W, crres, crpred, cbres,
+                                                                             cbpred, modes);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return VCS_OK;
+}
+
+// which: 0 luma4x4, 1 luma16x16 (planes: Y), 2 chroma8x8 (planes: Cr then Cb).  Host buffers.
+int vcs_intra_host(vcs_ctx *ctx, int which, int H, int W, const uint8_t *p0, const uint8_t *p1, int32_t *res0,
+                   int32_t *pred0, int32_t *res1, int32_t *pred1, uint8_t *modes) {
+    if (!ctx) return VCS_E_INVALID;
+    if (which < 0 || which > 2) return fail(ctx, VCS_E_INVALID, "which must be 0, 1 or 2");
+    const int m = which == 0 ? 4 : (which == 1 ? 16 : 8);
+    int rc = intra_check(ctx, H, W, m, p0, modes);
+    if (rc) return rc;
+    if (!res0 || !pred0 || (which == 2 && (!p1 || !res1 || !pred1))) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    const size_t n = (size_t)H * W, nm = (size_t)(H / m) * (W / m);
+    uint8_t *d_in, *d_modes; int32_t *d_out;
+    if ((rc = dev_buf(ctx, S_FRAMES, 2 * n, (void **)&d_in))) return rc;
+    if ((rc = dev_buf(ctx, S_COEF, 4 * n * 4, (void **)&d_out))) return rc;
+    if ((rc = dev_buf(ctx, S_FLAGS, nm, (void **)&d_modes))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(d_in, p0, n, cudaMemcpyHostToDevice, st));
+    if (which == 2) CK(ctx, cudaMemcpyAsync(d_in + n, p1, n, cudaMemcpyHostToDevice, st));
+    if (which == 0) rc = vcs_intra_luma4x4_dev(ctx, H, W, d_in, d_out, d_out + n, d_modes);
+    else if (which == 1) rc = vcs_intra_luma16x16_dev(ctx, H, W, d_in, d_out, d_out + n, d_modes);
+    else rc = vcs_intra_chroma8x8_dev(ctx, H, W, d_in, d_in + n, d_out, d_out + n, d_out + 2 * n, d_out + 3 * n, d_modes);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(res0, d_out, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(pred0, d_out + n, n * 4, cudaMemcpyDeviceToHost, st));
+    if (which == 2) {
+        CK(ctx, cudaMemcpyAsync(res1, d_out + 2 * n, n * 4, cudaMemcpyDeviceToHost, st));
+        CK(ctx, cudaMemcpyAsync(pred1, d_out + 3 * n, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(ctx, cudaMemcpyAsync(modes, d_modes, nm, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
     return VCS_OK;
 }
 

@@ -4,7 +4,7 @@
 Workload (BASELINE.json configs[1], SURVEY 8d "C2"): synthetic 1080p 8-bit 60-frame clip
 (I-P-P-P: 15 I + 45 P), 16x16 macroblocks, +/-16 step-1 full search with the reference's own
 cost (wrapped uint8 difference, motion.py:146) and static test (threshold 2000, motion.py:113),
-motion-compensated residual, 8x8 DCT, quantise QF=50 (rint -> int16 indices), dequantise, IDCT,
+motion-compensated residual, 8x8 DCT, quantise QF=50 (rint -> int8 indices, lossless at this QF), dequantise, IDCT,
 reconstruction.  One "step" = one pass over one such clip per GPU; `value` = frames of all ranks
 / max-over-ranks device time with the clip resident in HBM; `e2e` = the same through
 vcs_encode_clip_host with pinned HOST buffers (H2D of the clip and D2H of MVs + indices inside
@@ -42,9 +42,9 @@ def px_ops_per_p_frame(H, W, bs, R):
     return n_axis(W) * n_axis(H) * 3 * bs * bs
 
 
-def dct_bytes_per_p_frame(H, W, coef_bytes=2, recon=True):
+def dct_bytes_per_p_frame(H, W, coef_bytes=1, recon=True):
     """Algorithmic HBM bytes of the residual/DCT/recon kernel per frame: cur 3 + ref 3 + coef
-    3*coef_bytes + recon 3 per pixel (15 B/px with int16 indices)."""
+    3*coef_bytes + recon 3 per pixel (15 B/px with int16 indices, 12 B/px with int8)."""
     return H * W * (3 + 3 + 3 * coef_bytes + (3 if recon else 0))
 
 
@@ -150,7 +150,7 @@ def run_reference(args, rank, world):
 def workload_config():
     return {"workload": "C2: synthetic 1080p 60-frame clip (15 I + 45 P, I-P-P-P), 16x16 MB, +/-16 step-1 "
                         "full search, reference cost (wrapped u8 diff) + static test thr 2000, residual, "
-                        "8x8 DCT f64, quant QF50 -> int16 indices, dequant, IDCT, recon",
+                        "8x8 DCT f64, quant QF50 -> int8 indices (lossless: |idx| <= 1024/min(Q) = 102), dequant, IDCT, recon",
             "H": H, "W": W, "frames_per_clip": T, "clips_per_step": "one per GPU", "block": BS, "range": R,
             "gop": GOP, "qf": QF, "metric": "wrap8", "static_thr": STATIC_THR,
             "cache": "inputs (373 MB clip) larger than the 126 MB L2; no flush needed",
@@ -217,7 +217,7 @@ def run_b200(args, rank, world, local_rank):
 
     def measure(metric):
         ce = v.ClipEncoder([H, W], block_size=BS, search="full", search_range=R, gop_len=GOP, qf=QF,
-                           metric=metric, static_thr=STATIC_THR, coef_mode=v.COEF_I16_RINT, device=local_rank)
+                           metric=metric, static_thr=STATIC_THR, coef_mode=v.COEF_I8_RINT, device=local_rank)
         ctx = ce.ctx
         dout = ce.alloc_device_outputs(T, want_coef=True, want_recon=True)
         mv_bytes = dout["mv"].view(torch.uint8)           # NCCL carries bytes (torch has no int16 NCCL type)

@@ -45,6 +45,8 @@ extern "C" {
 #define VCS_COEF_F64 0      /* float64 planes, D/Q un-rounded: DCTcompressor.py:71 */
 #define VCS_COEF_F64_RINT 1 /* float64 planes, np.round(D/Q): DCTCompression/dct.py:179 */
 #define VCS_COEF_I16_RINT 2 /* the same integers as int16 planes (compact wire format) */
+#define VCS_COEF_I8_RINT 3  /* the same integers as int8 planes: |index| <= 1024/min(Q), so this is lossless
+                               exactly when min(Q) >= 9 (e.g. QF <= 50); refused with VCS_E_INVALID otherwise */
 
 /* which ME kernel a call may use */
 #define VCS_ME_AUTO 0    /* tiled full-search kernel when step==1 and bs is 8 or 16 */
@@ -137,7 +139,7 @@ int vcs_add_wrap_host(vcs_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n
 /* ---- 8x8 DCT / quantise / dequantise / IDCT ---------------------------------------------- */
 /* DCTCompressor.compress (DCTcompressor.py:49-74; rounded: dct.py:169-186).  H, W must be
  * multiples of 8 (the reference would bilinear-resize; VCS_E_INVALID here).  coef: 3 planes
- * H x W of float64 (VCS_COEF_F64*) or int16 (VCS_COEF_I16_RINT), order Y, Cr, Cb. */
+ * H x W of float64 (VCS_COEF_F64*), int16 (VCS_COEF_I16_RINT) or int8 (VCS_COEF_I8_RINT), order Y, Cr, Cb. */
 int vcs_compress_dev(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, int coef_mode, void *coef);
 int vcs_compress_host(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, int coef_mode, void *coef);
 /* DCTCompressor.decompress (DCTcompressor.py:76-93): planes -> BGR uint8.  If pred != NULL the

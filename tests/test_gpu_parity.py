@@ -155,7 +155,7 @@ def test_encoder_decoder_dropin(vcs, orc):
         assert fr.ref_i == n // 4 and fr.i == n
 
 
-@pytest.mark.parametrize("coef_mode", [0, 1, 2])
+@pytest.mark.parametrize("coef_mode", [0, 1, 2, 3])
 def test_clip_api_host_and_device(vcs, orc, coef_mode):
     """Whole-clip C-ABI calls (host buffers and device tensors) vs per-frame oracle."""
     import torch
@@ -277,7 +277,7 @@ def test_error_behaviour(vcs):
         mp.reconstruct_from_motion_vectors([[-100, 0]] * 64, buf, mp._block_coords().tolist())
 
 
-@pytest.mark.parametrize("coef_mode", [0, 2])
+@pytest.mark.parametrize("coef_mode", [0, 2, 3])
 def test_clip_decoder_roundtrip(vcs, orc, coef_mode):
     """Decoder side for a whole clip (decoder.py:52-69): MC from the original I-frames + decompress
     + wrap add == the encoder's own reconstruction == the oracle, bit for bit (host and device)."""
@@ -314,3 +314,20 @@ def test_sparsity_on_device(vcs, golden, golden_meta, qf):
     assert vcs.sparsity_device(ctx, idx, vcs.COEF_I16_RINT) == golden_meta[f"still_q{qf}_sparsity"]
     pl = torch.from_numpy(np.stack(dc.compress(img, rounded=True))).cuda()
     assert vcs.sparsity_device(ctx, pl, vcs.COEF_F64_RINT) == golden_meta[f"still_q{qf}_sparsity"]
+
+
+def test_int8_indices_refused_when_lossy(vcs):
+    """VCS_COEF_I8_RINT is only offered when |index| <= 1024/min(Q) fits int8 (min Q >= 9)."""
+    from vcs_h264_b200 import synth
+    clip = synth.clip(2, 32, 48, seed=1, margin=32)
+    for qf, ok in ((50.0, True), (10.0, True), (75.0, False), (99.0, False)):
+        ce = vcs.ClipEncoder([32, 48], block_size=16, search="full", search_range=4, gop_len=2, qf=qf,
+                             coef_mode=vcs.COEF_I8_RINT)
+        if ok:
+            out = ce.encode_host(clip)
+            ref = vcs.ClipEncoder([32, 48], block_size=16, search="full", search_range=4, gop_len=2, qf=qf,
+                                  coef_mode=vcs.COEF_I16_RINT).encode_host(clip)
+            assert np.array_equal(np.asarray(out["coef"]).astype(np.int16), np.asarray(ref["coef"]))
+        else:
+            with pytest.raises(vcs.VcsError):
+                ce.encode_host(clip)

@@ -47,7 +47,28 @@ def main():
                      "compress_GBps": px * (3 + 6) / (times["compress"] * 1e-3) / 1e9,
                      "decompress_GBps": px * (6 + 3) / (times["decompress"] * 1e-3) / 1e9,
                      "sparsity": sp, "psnr_db": psnr})
-    print(json.dumps({"workload": "synthetic 2160x3840 stills, 8x8 DCT f64, rint quantiser -> int16", "rows": rows}))
+    # intra mode decision on the same 4K still (IntraframeCompression/intraframe.py:24-317)
+    from oracle import oracle as orc   # colour split only (test-side helper, not timed)
+    ycc = orc.bgr2ycrcb(stills[0].cpu().numpy())
+    Y, Cr, Cb = (torch.from_numpy(np.ascontiguousarray(ycc[..., k])).cuda() for k in range(3))
+    o = [torch.empty((H, W), dtype=torch.int32, device="cuda") for _ in range(4)]
+    m4 = torch.empty((H // 4, W // 4), dtype=torch.uint8, device="cuda")
+    intra = {}
+    for name, fn in (("luma4x4", lambda: ctx.call("vcs_intra_luma4x4_dev", H, W, _capi.ptr(Y), _capi.ptr(o[0]), _capi.ptr(o[1]), _capi.ptr(m4))),
+                     ("luma16x16", lambda: ctx.call("vcs_intra_luma16x16_dev", H, W, _capi.ptr(Y), _capi.ptr(o[0]), _capi.ptr(o[1]), _capi.ptr(m4))),
+                     ("chroma8x8", lambda: ctx.call("vcs_intra_chroma8x8_dev", H, W, _capi.ptr(Cr), _capi.ptr(Cb), _capi.ptr(o[0]), _capi.ptr(o[1]), _capi.ptr(o[2]), _capi.ptr(o[3]), _capi.ptr(m4)))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        intra[name + "_ms"] = e0.elapsed_time(e1) / 10
+    print(json.dumps({"workload": "synthetic 2160x3840 stills, 8x8 DCT f64, rint quantiser -> int16", "rows": rows,
+                      "intra_4k": intra}))
 
 
 if __name__ == "__main__":

@@ -4,7 +4,7 @@ IDCT reconstruction, behind the reference's own class surface (MotionProcessor, 
 Encoder, Decoder, Frame) plus a clip-level batched API (ClipEncoder).  CUDA only: importing works
 anywhere, every operation needs libvcs_b200.so and a GPU."""
 from . import _capi
-from ._capi import (COEF_F64, COEF_F64_RINT, COEF_I16_RINT, METRIC_SAD, METRIC_WRAP8, ME_AUTO,
+from ._capi import (COEF_F64, COEF_F64_RINT, COEF_I16_RINT, COEF_I8_RINT, METRIC_SAD, METRIC_WRAP8, ME_AUTO,
                     ME_GENERIC, ME_TILED, VcsError)
 from .frame import Frame
 from .motion import MotionProcessor

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libvcs_b200.so")
 OK = 0
 METRIC_WRAP8, METRIC_SAD = 0, 1
 MB_STATIC, MB_NOCAND = 1, 2
-COEF_F64, COEF_F64_RINT, COEF_I16_RINT = 0, 1, 2
+COEF_F64, COEF_F64_RINT, COEF_I16_RINT, COEF_I8_RINT = 0, 1, 2, 3
 ME_AUTO, ME_GENERIC, ME_TILED = 0, 1, 2
 
 

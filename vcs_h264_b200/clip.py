@@ -14,7 +14,7 @@ from . import _capi
 from .runtime import get_context
 
 COEF_DTYPES = {_capi.COEF_F64: np.float64, _capi.COEF_F64_RINT: np.float64,
-               _capi.COEF_I16_RINT: np.int16}
+               _capi.COEF_I16_RINT: np.int16, _capi.COEF_I8_RINT: np.int8}
 
 
 class ClipEncoder:
@@ -65,7 +65,7 @@ class ClipEncoder:
         out = dict(mv=buf((nP, self.N, 2), torch.int16), cost=buf((nP, self.N), torch.int32),
                    flags=buf((nP, self.N), torch.uint8))
         if want_coef:
-            dt = torch.int16 if self.coef_mode == _capi.COEF_I16_RINT else torch.float64
+            dt = {_capi.COEF_I16_RINT: torch.int16, _capi.COEF_I8_RINT: torch.int8}.get(self.coef_mode, torch.float64)
             out["coef"] = buf((nP, 3, self.H, self.W), dt)
         if want_recon:
             out["recon"] = buf((nP, self.H, self.W, 3), torch.uint8)
@@ -94,7 +94,7 @@ class ClipEncoder:
                    cost=torch.empty((nP, self.N), dtype=torch.int32, device=dev),
                    flags=torch.empty((nP, self.N), dtype=torch.uint8, device=dev))
         if want_coef:
-            dt = torch.int16 if self.coef_mode == _capi.COEF_I16_RINT else torch.float64
+            dt = {_capi.COEF_I16_RINT: torch.int16, _capi.COEF_I8_RINT: torch.int8}.get(self.coef_mode, torch.float64)
             out["coef"] = torch.empty((nP, 3, self.H, self.W), dtype=dt, device=dev)
         if want_recon:
             out["recon"] = torch.empty((nP, self.H, self.W, 3), dtype=torch.uint8, device=dev)

@@ -253,6 +253,9 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                             if (coef_mode == 2) {
                                 const uint32_t h = (uint32_t)(uint16_t)(int16_t)(int)v;
                                 if (j & 1) pk[ch][j >> 1] |= h << 16; else pk[ch][j >> 1] = h;
+                            } else if (coef_mode == 3) {   // int8: lossless when 1024 / min(Q) <= 127 (checked on the host)
+                                const uint32_t h = (uint32_t)(uint8_t)(int8_t)(int)v;
+                                if (j & 3) pk[ch][j >> 2] |= h << (8 * (j & 3)); else pk[ch][j >> 2] = h;
                             } else if (j & 1) {
                                 *reinterpret_cast<double2 *>(reinterpret_cast<double *>(a.coef) + gidx0 + ch * npix + j - 1) =
                                     make_double2(dprev[ch], v);
@@ -268,6 +271,11 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     for (int ch = 0; ch < 3; ++ch)
                         *reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(a.coef) + gidx0 + ch * npix) =
                             make_uint4(pk[ch][0], pk[ch][1], pk[ch][2], pk[ch][3]);
+                } else if (a.coef && coef_mode == 3) {
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch)
+                        *reinterpret_cast<uint2 *>(reinterpret_cast<int8_t *>(a.coef) + gidx0 + ch * npix) =
+                            make_uint2(pk[ch][0], pk[ch][1]);
                 }
             }
         } else if (do_inverse && row_on) {
@@ -280,6 +288,10 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int j = 0; j < 8; ++j) qv[j] = (double)(int)(int16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
+                } else if (coef_mode == 3) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(reinterpret_cast<const int8_t *>(a.coef) + gidx0 + ch * npix);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) qv[j] = (double)(int)(int8_t)(((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xff);
                 } else {
                     const double *o = reinterpret_cast<const double *>(a.coef) + gidx0 + ch * npix;
 #pragma unroll
@@ -404,7 +416,8 @@ template <int ELEM>
 __global__ void count_nonzero_kernel(const void *__restrict__ coef, size_t n, unsigned long long *__restrict__ out) {
     unsigned long long c = 0;
     for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
-        if (ELEM == 2) c += reinterpret_cast<const int16_t *>(coef)[k] != 0;
+        if (ELEM == 1) c += reinterpret_cast<const int8_t *>(coef)[k] != 0;
+        else if (ELEM == 2) c += reinterpret_cast<const int16_t *>(coef)[k] != 0;
         else c += reinterpret_cast<const double *>(coef)[k] != 0.0;
     }
 #pragma unroll

@@ -165,7 +165,14 @@ int launch_dct(vcs_ctx *ctx, cudaStream_t st, DctArgs &a, int nP) {
     if (a.H <= 0 || a.W <= 0 || a.H % 8 || a.W % 8)
         return fail(ctx, VCS_E_INVALID,
                     "H=%d W=%d must be multiples of 8 (the reference resizes, DCTcompressor.py:52)", a.H, a.W);
-    if (a.coef_mode < 0 || a.coef_mode > 2) return fail(ctx, VCS_E_INVALID, "coef_mode %d", a.coef_mode);
+    if (a.coef_mode < 0 || a.coef_mode > 3) return fail(ctx, VCS_E_INVALID, "coef_mode %d", a.coef_mode);
+    if (a.coef_mode == VCS_COEF_I8_RINT) {
+        // |D| <= 8 * 128 = 1024 for inputs in [-128,127], so |index| <= 1024 / min(Q): int8 is lossless iff that fits
+        double qmin = ctx->h_Q[0];
+        for (int k = 1; k < 192; ++k) qmin = ctx->h_Q[k] < qmin ? ctx->h_Q[k] : qmin;
+        if (1024.0 / qmin > 127.0)
+            return fail(ctx, VCS_E_INVALID, "int8 indices are not lossless for this Q (min %g < 9): use VCS_COEF_I16_RINT", qmin);
+    }
     if (nP <= 0) return VCS_OK;
     a.Q = ctx->d_Q;
     // persistent warps: 4 CTAs of 4 warps per SM, each warp walks 8x32-pixel tiles
@@ -178,7 +185,7 @@ int launch_dct(vcs_ctx *ctx, cudaStream_t st, DctArgs &a, int nP) {
     return VCS_OK;
 }
 
-size_t coef_elem(int coef_mode) { return coef_mode == VCS_COEF_I16_RINT ? 2 : 8; }
+size_t coef_elem(int coef_mode) { return coef_mode == VCS_COEF_I8_RINT ? 1 : (coef_mode == VCS_COEF_I16_RINT ? 2 : 8); }
 
 EvTriple *next_events(vcs_ctx *ctx) {
     if (!ctx->timing) return nullptr;
@@ -540,7 +547,7 @@ int vcs_compress_dev(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, int coef_mo
 int vcs_compress_host(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, int coef_mode, void *coef) {
     if (!ctx) return VCS_E_INVALID;
     if (!bgr || !coef) return fail(ctx, VCS_E_INVALID, "NULL argument");
-    if (H <= 0 || W <= 0 || H % 8 || W % 8 || coef_mode < 0 || coef_mode > 2)
+    if (H <= 0 || W <= 0 || H % 8 || W % 8 || coef_mode < 0 || coef_mode > 3)
         return fail(ctx, VCS_E_INVALID, "H=%d W=%d must be multiples of 8; coef_mode=%d", H, W, coef_mode);
     const size_t npix = (size_t)H * W;
     uint8_t *d_img; void *d_coef; int rc;
@@ -569,7 +576,7 @@ int vcs_decompress_host(vcs_ctx *ctx, int H, int W, int coef_mode, const void *c
                         uint8_t *bgr) {
     if (!ctx) return VCS_E_INVALID;
     if (!coef || !bgr) return fail(ctx, VCS_E_INVALID, "NULL argument");
-    if (H <= 0 || W <= 0 || H % 8 || W % 8 || coef_mode < 0 || coef_mode > 2)
+    if (H <= 0 || W <= 0 || H % 8 || W % 8 || coef_mode < 0 || coef_mode > 3)
         return fail(ctx, VCS_E_INVALID, "H=%d W=%d must be multiples of 8; coef_mode=%d", H, W, coef_mode);
     const size_t npix = (size_t)H * W;
     uint8_t *d_img; void *d_coef; int rc;
@@ -621,7 +628,7 @@ int vcs_decode_clip_host(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_
     if (!ctx) return VCS_E_INVALID;
     if (!ref_frames || !mv || !coef || !recon || gop_len < 2 || T < 1 || bs <= 0 || H < bs || W < bs)
         return fail(ctx, VCS_E_INVALID, "bad decode arguments");
-    if (H % 8 || W % 8 || coef_mode < 0 || coef_mode > 2)
+    if (H % 8 || W % 8 || coef_mode < 0 || coef_mode > 3)
         return fail(ctx, VCS_E_INVALID, "H=%d W=%d must be multiples of 8; coef_mode=%d", H, W, coef_mode);
     const size_t fs = (size_t)H * W * 3, npix = (size_t)H * W, ce = coef_elem(coef_mode);
     const int N = vcs_num_blocks(H, W, bs), nP = vcs_num_p_frames(T, gop_len), nG = (T + gop_len - 1) / gop_len;
@@ -650,7 +657,7 @@ int vcs_decode_clip_host(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_
 // numerator of dct.py:188-191's sparsity: number of non-zero coefficients in n elements (device pointer)
 int vcs_count_nonzero_dev(vcs_ctx *ctx, int coef_mode, const void *coef, size_t n, unsigned long long *count_host) {
     if (!ctx) return VCS_E_INVALID;
-    if (!coef || !count_host || coef_mode < 0 || coef_mode > 2) return fail(ctx, VCS_E_INVALID, "bad arguments");
+    if (!coef || !count_host || coef_mode < 0 || coef_mode > 3) return fail(ctx, VCS_E_INVALID, "bad arguments");
     unsigned long long *d_cnt; int rc;
     if ((rc = dev_buf(ctx, S_CYC, 8, (void **)&d_cnt))) return rc;
     cudaStream_t st = ctx->stream;
@@ -658,7 +665,8 @@ int vcs_count_nonzero_dev(vcs_ctx *ctx, int coef_mode, const void *coef, size_t 
     if (n) {
         int blocks = (int)((n + 1023) / 1024);
         if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-        if (coef_mode == VCS_COEF_I16_RINT) count_nonzero_kernel<2><<<blocks, 256, 0, st>>>(coef, n, d_cnt);
+        if (coef_mode == VCS_COEF_I8_RINT) count_nonzero_kernel<1><<<blocks, 256, 0, st>>>(coef, n, d_cnt);
+        else if (coef_mode == VCS_COEF_I16_RINT) count_nonzero_kernel<2><<<blocks, 256, 0, st>>>(coef, n, d_cnt);
         else count_nonzero_kernel<8><<<blocks, 256, 0, st>>>(coef, n, d_cnt);
         CK(ctx, cudaGetLastError());
         ctx->launches += 1;

@@ -180,6 +180,21 @@ def cpu_baseline_sample(min_seconds=10.0):
                       f"oracle/vcs_oracle.c: SSE2 costs, OpenMP over macroblocks, {dt:.1f} s"}
 
 
+def parity_spot_check(clip, first_p, strip=96):
+    """Outside the timed region: the first P-frame's top `strip` rows against the CPU oracle.
+    MVs / costs / quantised indices / reconstruction are integers: any mismatch is a flip."""
+    from oracle import oracle as orc
+    o = orc.encode_p(clip[1][:strip + R + BS], clip[0][:strip + R + BS], BS, metric=orc.METRIC_WRAP8,
+                     static_thr=STATIC_THR, Q=orc.qtables(QF), round_mode=1, **orc.symmetric_search_params(R))
+    n = (strip // BS) * (W // BS)
+    return {"rows": strip,
+            "mv_mismatch": int((first_p["mv"].astype(np.int32)[:n] != o["mv"][:n]).any(1).sum()),
+            "cost_mismatch": int((first_p["cost"].view(np.uint32)[:n] != o["cost"][:n]).sum()),
+            "index_flips": int((first_p["coef"][:, :strip].astype(np.float64) != o["planes"][:, :strip]).sum()),
+            "recon_pixel_mismatch": int((first_p["recon"][:strip] != o["recon"][:strip]).sum()),
+            "arithmetic": "float64 DCT with the reference's operation order: flips are 0 by construction"}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
     import torch
@@ -265,7 +280,8 @@ def run_b200(args, rank, world, local_rank):
         same = bool(torch.equal(hout["mv"], dout["mv"].cpu()) and torch.equal(hout["coef"], dout["coef"].cpu()))
         h2d = host_in.numel()
         d2h = sum(hout[k].numel() * hout[k].element_size() for k in ("mv", "cost", "flags", "coef"))
-        return dict(ms=ms, launches=launches, me_ms=me_ms / max(ncalls, 1), dct_ms=dct_ms / max(ncalls, 1),
+        first_p = {k: dout[k][0].cpu().numpy() for k in ("mv", "cost", "coef", "recon")}
+        return dict(first_p=first_p, ms=ms, launches=launches, me_ms=me_ms / max(ncalls, 1), dct_ms=dct_ms / max(ncalls, 1),
                     e2e_fps=world * T * args.steps / dt, e2e_ms=1e3 * dt / args.steps, h2d=h2d, d2h=d2h,
                     clocks=clocks, static_frac=static_frac, host_equals_device=same)
 
@@ -295,10 +311,14 @@ def run_b200(args, rank, world, local_rank):
     pxops = px_ops_per_p_frame(H, W, BS, R) * nP           # per ME launch (one clip)
     peak_pxops = mb["vabsdiff4_acc"]["warp_instr_per_s"] * 32 * 4
 
+    # DRAM bytes per launch from the ncu --set full capture of this command (profiles/r1_ncu_full_summary.csv)
+    ME_TRAFFIC, DCT_TRAFFIC = 381.6e6, 904.9e6
+
     def me_roof(m):
         ach = pxops / (m["me_ms"] * 1e-3)
-        return {"bound": "int32", "kernel": "me search (one launch = 45 P-frames)", "achieved": ach / 1e9,
-                "peak": peak_pxops / 1e9, "unit": "Gpxop/s", "frac": ach / peak_pxops, "traffic": None,
+        return {"bound": "int32", "kernel": "me_tiled_kernel (one launch = 45 P-frames)", "achieved": ach / 1e9,
+                "peak": peak_pxops / 1e9, "unit": "Gpxop/s", "frac": ach / peak_pxops, "traffic": ME_TRAFFIC,
+                "traffic_unit": "bytes of DRAM traffic per launch (ncu); algorithmic input 373.2e6",
                 "ms_per_launch": m["me_ms"],
                 "peak_source": "VABSDIFF4.U8.ACC issue rate measured in this run x 32 lanes x 4 bytes"}
 
@@ -306,7 +326,8 @@ def run_b200(args, rank, world, local_rank):
         b = dct_bytes_per_p_frame(H, W) * nP
         ach = b / (m["dct_ms"] * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": "dct_stage_kernel (one launch = 45 P-frames)", "achieved": ach,
-                "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": DCT_TRAFFIC,
+                "algorithmic_bytes": b, "note": "FP64-pipe bound before HBM (96 DFMA/px, bit-exact float64 DCT)",
                 "ms_per_launch": m["dct_ms"], "peak_source": hbm_src}
 
     line = {
@@ -327,6 +348,7 @@ def run_b200(args, rank, world, local_rank):
                             "roofline": me_roof(sad), "clocks": sad["clocks"]}
     if world == 1 and not args.skip_cpu:
         line["cpu_baseline"] = cpu_baseline_sample()
+        line["parity_check"] = parity_spot_check(clip_np, wrap["first_p"])
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -103,6 +103,32 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads (and so its first-touched pinned buffers) to the CPUs local to its GPU:
+    with 8 ranks the end-to-end path is bound by host memory / PCIe root-complex bandwidth, and a rank whose
+    staging memory sits on the other socket halves its copy rate.  Best effort; returns the cpulist or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:           # NVML pads the PCI domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpulist
+    except Exception:
+        pass
+    return None
+
+
 def make_clip(seed):
     from vcs_h264_b200 import synth
     return synth.clip(T, H, W, seed=seed)
@@ -203,6 +229,7 @@ def run_b200(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation (first touch)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -314,9 +341,15 @@ def run_b200(args, rank, world, local_rank):
     # DRAM bytes per launch from the ncu --set full capture of this command (profiles/r1_ncu_full_summary.csv)
     ME_TRAFFIC, DCT_TRAFFIC = 381.6e6, 904.9e6
 
-    def me_roof(m):
+    sm_count = ctx0.device_info()["sm_count"]
+
+    def me_roof(m, instr_per_word=1):
         ach = pxops / (m["me_ms"] * 1e-3)
-        return {"bound": "int32", "kernel": "me_tiled_kernel (one launch = 45 P-frames)", "achieved": ach / 1e9,
+        # issue-slot view: the cost needs `instr_per_word` warp instructions per 4 bytes at best; one
+        # scheduler issues one instruction per clock (4 per SM)
+        issue_peak = sm_count * 4 * (wrap["clocks"]["sm_mhz"] or 1965.0) * 1e6
+        issue_frac = (pxops / 4 / 32 * instr_per_word) / (m["me_ms"] * 1e-3) / issue_peak
+        return {"min_instr_per_word": instr_per_word, "frac_of_issue_slots": issue_frac,"bound": "int32", "kernel": "me_tiled_kernel (one launch = 45 P-frames)", "achieved": ach / 1e9,
                 "peak": peak_pxops / 1e9, "unit": "Gpxop/s", "frac": ach / peak_pxops, "traffic": ME_TRAFFIC,
                 "traffic_unit": "bytes of DRAM traffic per launch (ncu); algorithmic input 373.2e6",
                 "ms_per_launch": m["me_ms"],
@@ -339,8 +372,8 @@ def run_b200(args, rank, world, local_rank):
                 "d2h_bytes_per_step": wrap["d2h"], "ms_per_step": wrap["e2e_ms"],
                 "host_equals_device": wrap["host_equals_device"]},
         "gpu_launches": wrap["launches"],
-        "roofline": me_roof(wrap), "roofline_dct": dct_roof(wrap),
-        "static_fraction": wrap["static_frac"], "microbench": mb,
+        "roofline": me_roof(wrap, 3), "roofline_dct": dct_roof(wrap),
+        "static_fraction": wrap["static_frac"], "microbench": mb, "host_numa_cpus_rank0": numa,
     }
     if sad is not None:
         line["sad_mode"] = {"value": world * T * args.steps / (sad["ms"] * 1e-3), "unit": "frames/s",

@@ -357,15 +357,20 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
                     }
                 }
             }
-            // first strict minimum in scan order: key = cost | global dy index | global dx index
-            unsigned long long best = ~0ull;
-            const unsigned long long xkey = (unsigned long long)(cx * ND + dxw);
+            // first strict minimum in scan order.  Within the thread dx is fixed, so (cost, dy) decides:
+            // a 32-bit key cost*64 + d (cost < 2^18 for bs <= 16, d < 64) reduced with integer min; the
+            // multiply-add runs on the FMA pipe, only the min and the validity select use the busy ALU pipe.
+            static_assert(ND <= 64 && 255 * 3 * BS * BS < (1 << 26), "32-bit key layout");
+            uint32_t k32 = 0xFFFFFFFFu;
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
-                const unsigned long long key =
-                    ((unsigned long long)acc[d] << 32) | ((unsigned long long)(cy * ND + d) << 16) | xkey;
-                if (((dymask >> d) & 1) && key < best) best = key;
+                const uint32_t k = ((dymask >> d) & 1) ? acc[d] * 64u + (uint32_t)d : 0xFFFFFFFFu;
+                k32 = min(k32, k);
             }
+            unsigned long long best = ~0ull;
+            if (k32 != 0xFFFFFFFFu)
+                best = ((unsigned long long)(k32 >> 6) << 32) | ((unsigned long long)(cy * ND + (int)(k32 & 63u)) << 16) |
+                       (unsigned long long)(cx * ND + dxw);
             atomicMin(&sBest[mb], best);
         }
         __syncthreads();   // search of this unit done: T may be overwritten, sBest is complete

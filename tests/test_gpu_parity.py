@@ -331,3 +331,17 @@ def test_int8_indices_refused_when_lossy(vcs):
         else:
             with pytest.raises(vcs.VcsError):
                 ce.encode_host(clip)
+
+
+def test_main_driver_frame_and_clip_modes_agree(vcs, orc):
+    """main.py's loop (main.py:29-50): per-frame drop-in classes and the clip path give the same decoded
+    frames as the oracle."""
+    from vcs_h264_b200 import main as drv, synth
+    clip = synth.clip(7, 64, 96, seed=3, margin=32)
+    frames = [clip[t] for t in range(7)]
+    _, dec_f = drv.run(frames, block_size=8, mode="frame")
+    _, dec_c = drv.run(frames, block_size=8, mode="clip")
+    prm = orc.reference_search_params(8)
+    for t in range(7):
+        want = frames[t] if t % 4 == 0 else orc.encode_p(frames[t], frames[(t // 4) * 4], 8, **prm)["recon"]
+        assert np.array_equal(dec_f[t], want) and np.array_equal(dec_c[t], want)

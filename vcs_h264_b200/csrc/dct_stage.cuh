@@ -42,9 +42,10 @@ __constant__ double c_dct[64];  // _dctMatrix(), row-major, computed on the host
 
 constexpr int DCT_TILE_W = 32;                        // pixels per warp tile row (4 blocks)
 constexpr int DCT_WARPS = 4;                          // warps per CTA, each with a private tile
+constexpr int DCT_NCH = 1;                            // channels per pass group (1 or 3)
 constexpr int DCT_THREADS = 32 * DCT_WARPS;
 constexpr int DCT_RS = DCT_TILE_W + 1;                // row stride of the double tiles: conflict-free
-constexpr int DCT_X_DOUBLES = 3 * 8 * DCT_RS;         // per-warp transform tile [3][8][RS]
+constexpr int DCT_X_DOUBLES = DCT_NCH * 8 * DCT_RS;   // per-warp transform tile [NCH][8][RS]
 constexpr int DCT_PLANE = 8 * DCT_TILE_W * 3;         // bytes of one 8 x 32 x 3 byte tile
 constexpr size_t DCT_WARP_BYTES = (size_t)DCT_X_DOUBLES * sizeof(double) + 3 * DCT_PLANE;
 constexpr size_t DCT_SMEM_BYTES = 2 * 192 * sizeof(double) + DCT_WARPS * DCT_WARP_BYTES;
@@ -87,7 +88,7 @@ __device__ __forceinline__ void load24(const uint8_t *p, uint32_t w[6]) {
 
 __device__ __forceinline__ uint32_t byte_of(const uint32_t *w, int k) { return (w[k >> 2] >> (8 * (k & 3))) & 0xffu; }
 
-__global__ void __launch_bounds__(DCT_THREADS, 4)
+__global__ void __launch_bounds__(DCT_THREADS, DCT_NCH == 1 ? 6 : 4)
 dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     extern __shared__ __align__(16) unsigned char dct_smem[];
     double *s_q = reinterpret_cast<double *>(dct_smem);          // Q [3][64]
@@ -195,93 +196,101 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
         __syncwarp();
 
         const size_t gidx0 = (size_t)p * 3 * npix + (size_t)(y0 + rp_i) * W + x0 + rp_blk * 8;   // + ch * npix
+        // Passes B-E run for NCH channels at a time (outer loop not unrolled): NCH = 3 fetches every DCT-matrix
+        // constant once per 3 chains but needs ~120 registers and 3x the code; NCH = 1 halves both.
+#pragma unroll 1
+        for (int ch0 = 0; ch0 < 3; ch0 += DCT_NCH) {
         if (forward) {
-            // ---- B: column pass  T = C . X  (T[i][j] = sum_k C[i][k] X[k][j]), 3 channels per lane ------
+            // ---- B: column pass  T = C . X  (T[i][j] = sum_k C[i][k] X[k][j]) -------------------------------
             if (col_on) {
-                double xk[3][8];
+                double xk[DCT_NCH][8];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
+                for (int c = 0; c < DCT_NCH; ++c)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) xk[ch][k] = (double)(int)s_in8[(ch * 8 + k) * DCT_TILE_W + lane];
+                    for (int k = 0; k < 8; ++k) xk[c][k] = (double)(int)s_in8[((ch0 + c) * 8 + k) * DCT_TILE_W + lane];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                    double s[DCT_NCH];
+#pragma unroll
+                    for (int c = 0; c < DCT_NCH; ++c) s[c] = 0.0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double c = c_dct[i * 8 + k];
-                        s0 = __fma_rn(c, xk[0][k], s0);
-                        s1 = __fma_rn(c, xk[1][k], s1);
-                        s2 = __fma_rn(c, xk[2][k], s2);
+                        const double cc = c_dct[i * 8 + k];
+#pragma unroll
+                        for (int c = 0; c < DCT_NCH; ++c) s[c] = __fma_rn(cc, xk[c][k], s[c]);
                     }
-                    s_x[(0 * 8 + i) * DCT_RS + lane] = s0;
-                    s_x[(1 * 8 + i) * DCT_RS + lane] = s1;
-                    s_x[(2 * 8 + i) * DCT_RS + lane] = s2;
+#pragma unroll
+                    for (int c = 0; c < DCT_NCH; ++c) s_x[(c * 8 + i) * DCT_RS + lane] = s[c];
                 }
             }
             __syncwarp();
             // ---- C: row pass  D = T . C^T  (D[i][j] = sum_k T[i][k] C[j][k]); quantise; store ------------
             if (row_on) {
-                double tk[3][8];
+                double tk[DCT_NCH][8];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
+                for (int c = 0; c < DCT_NCH; ++c)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) tk[ch][k] = s_x[ch * 8 * DCT_RS + rbase0 + k];
-                uint32_t pk[3][4];
-                double dprev[3] = {0.0, 0.0, 0.0};
+                    for (int k = 0; k < 8; ++k) tk[c][k] = s_x[c * 8 * DCT_RS + rbase0 + k];
+                uint32_t pk[DCT_NCH][4];
+                double dprev[DCT_NCH];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    double s[3] = {0.0, 0.0, 0.0};
+                    double s[DCT_NCH];
+#pragma unroll
+                    for (int c = 0; c < DCT_NCH; ++c) s[c] = 0.0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double c = c_dct[j * 8 + k];
+                        const double cc = c_dct[j * 8 + k];
 #pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) s[ch] = __fma_rn(tk[ch][k], c, s[ch]);
+                        for (int c = 0; c < DCT_NCH; ++c) s[c] = __fma_rn(tk[c][k], cc, s[c]);
                     }
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
+                    for (int c = 0; c < DCT_NCH; ++c) {
+                        const int ch = ch0 + c;
                         const double Q = s_q[ch * 64 + j * 8 + rp_i];
                         double v;
                         if (coef_mode == 0) {
-                            v = s[ch] / Q;                                 // np.true_divide (DCTcompressor.py:71)
+                            v = s[c] / Q;                                  // np.true_divide (DCTcompressor.py:71)
                         } else {
-                            const double q0 = s[ch] * s_rq[ch * 64 + j * 8 + rp_i];
+                            const double q0 = s[c] * s_rq[ch * 64 + j * 8 + rp_i];
                             v = rint(q0);                                  // np.round (dct.py:179) of RN(s/Q):
                             if (fabs(fabs(q0 - v) - 0.5) < 9.313225746154785e-10)   // 2^-30 of a half-integer
-                                v = rint(s[ch] / Q);                       // -> the exact quotient decides
+                                v = rint(s[c] / Q);                        // -> the exact quotient decides
                         }
                         if (a.coef) {
                             if (coef_mode == 2) {
                                 const uint32_t h = (uint32_t)(uint16_t)(int16_t)(int)v;
-                                if (j & 1) pk[ch][j >> 1] |= h << 16; else pk[ch][j >> 1] = h;
+                                if (j & 1) pk[c][j >> 1] |= h << 16; else pk[c][j >> 1] = h;
                             } else if (coef_mode == 3) {   // int8: lossless when 1024 / min(Q) <= 127 (checked on the host)
                                 const uint32_t h = (uint32_t)(uint8_t)(int8_t)(int)v;
-                                if (j & 3) pk[ch][j >> 2] |= h << (8 * (j & 3)); else pk[ch][j >> 2] = h;
+                                if (j & 3) pk[c][j >> 2] |= h << (8 * (j & 3)); else pk[c][j >> 2] = h;
                             } else if (j & 1) {
                                 *reinterpret_cast<double2 *>(reinterpret_cast<double *>(a.coef) + gidx0 + ch * npix + j - 1) =
-                                    make_double2(dprev[ch], v);
+                                    make_double2(dprev[c], v);
                             } else {
-                                dprev[ch] = v;
+                                dprev[c] = v;
                             }
                         }
-                        if (do_inverse) s_x[ch * 8 * DCT_RS + rbase0 + j] = v * Q;   // E = blk * Q (DCTcompressor.py:86)
+                        if (do_inverse) s_x[c * 8 * DCT_RS + rbase0 + j] = v * Q;   // E = blk * Q (DCTcompressor.py:86)
                     }
                 }
                 if (a.coef && coef_mode == 2) {
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch)
-                        *reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(a.coef) + gidx0 + ch * npix) =
-                            make_uint4(pk[ch][0], pk[ch][1], pk[ch][2], pk[ch][3]);
+                    for (int c = 0; c < DCT_NCH; ++c)
+                        *reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(a.coef) + gidx0 + (ch0 + c) * npix) =
+                            make_uint4(pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
                 } else if (a.coef && coef_mode == 3) {
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch)
-                        *reinterpret_cast<uint2 *>(reinterpret_cast<int8_t *>(a.coef) + gidx0 + ch * npix) =
-                            make_uint2(pk[ch][0], pk[ch][1]);
+                    for (int c = 0; c < DCT_NCH; ++c)
+                        *reinterpret_cast<uint2 *>(reinterpret_cast<int8_t *>(a.coef) + gidx0 + (ch0 + c) * npix) =
+                            make_uint2(pk[c][0], pk[c][1]);
                 }
             }
         } else if (do_inverse && row_on) {
             // inverse-only: E = coefficient planes * Q
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
+            for (int c = 0; c < DCT_NCH; ++c) {
+                const int ch = ch0 + c;
                 double qv[8];
                 if (coef_mode == 2) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const int16_t *>(a.coef) + gidx0 + ch * npix);
@@ -301,60 +310,67 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) s_x[ch * 8 * DCT_RS + rbase0 + j] = qv[j] * s_q[ch * 64 + j * 8 + rp_i];
+                for (int j = 0; j < 8; ++j) s_x[c * 8 * DCT_RS + rbase0 + j] = qv[j] * s_q[ch * 64 + j * 8 + rp_i];
             }
         }
         if (do_inverse) {
             __syncwarp();
             // ---- D: inverse column pass  T' = C^T . E  (T'[i][j] = sum_k C[k][i] E[k][j]) ---------------------
             if (col_on) {
-                double ek[3][8];
+                double ek[DCT_NCH][8];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
+                for (int c = 0; c < DCT_NCH; ++c)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) ek[ch][k] = s_x[(ch * 8 + k) * DCT_RS + lane];
+                    for (int k = 0; k < 8; ++k) ek[c][k] = s_x[(c * 8 + k) * DCT_RS + lane];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                    double s[DCT_NCH];
+#pragma unroll
+                    for (int c = 0; c < DCT_NCH; ++c) s[c] = 0.0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double c = c_dct[k * 8 + i];
-                        s0 = __fma_rn(c, ek[0][k], s0);
-                        s1 = __fma_rn(c, ek[1][k], s1);
-                        s2 = __fma_rn(c, ek[2][k], s2);
+                        const double cc = c_dct[k * 8 + i];
+#pragma unroll
+                        for (int c = 0; c < DCT_NCH; ++c) s[c] = __fma_rn(cc, ek[c][k], s[c]);
                     }
-                    s_x[(0 * 8 + i) * DCT_RS + lane] = s0;
-                    s_x[(1 * 8 + i) * DCT_RS + lane] = s1;
-                    s_x[(2 * 8 + i) * DCT_RS + lane] = s2;
+#pragma unroll
+                    for (int c = 0; c < DCT_NCH; ++c) s_x[(c * 8 + i) * DCT_RS + lane] = s[c];
                 }
             }
             __syncwarp();
             // ---- E: inverse row pass  P = T' . C ; truncating uint8 store ; +128 ---------------------------------
             if (row_on) {
-                double tk[3][8];
+                double tk[DCT_NCH][8];
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
+                for (int c = 0; c < DCT_NCH; ++c)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) tk[ch][k] = s_x[ch * 8 * DCT_RS + rbase0 + k];
-                uint32_t w[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+                    for (int k = 0; k < 8; ++k) tk[c][k] = s_x[c * 8 * DCT_RS + rbase0 + k];
+                uint32_t w[DCT_NCH][2];
+#pragma unroll
+                for (int c = 0; c < DCT_NCH; ++c) w[c][0] = w[c][1] = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    double s[3] = {0.0, 0.0, 0.0};
+                    double s[DCT_NCH];
+#pragma unroll
+                    for (int c = 0; c < DCT_NCH; ++c) s[c] = 0.0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double c = c_dct[k * 8 + j];
+                        const double cc = c_dct[k * 8 + j];
 #pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) s[ch] = __fma_rn(tk[ch][k], c, s[ch]);
+                        for (int c = 0; c < DCT_NCH; ++c) s[c] = __fma_rn(tk[c][k], cc, s[c]);
                     }
                     // float64 -> uint8 store (DCTcompressor.py:81,88): truncate toward zero, low 8 bits; then +128
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch)
-                        w[ch][j >> 2] |= (((uint32_t)(long long)s[ch] + 128u) & 0xffu) << (8 * (j & 3));
+                    for (int c = 0; c < DCT_NCH; ++c)
+                        w[c][j >> 2] |= (((uint32_t)(long long)s[c] + 128u) & 0xffu) << (8 * (j & 3));
                 }
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch)
-                    *reinterpret_cast<uint2 *>(s_out + (ch * 8 + rp_i) * DCT_TILE_W + rp_blk * 8) = make_uint2(w[ch][0], w[ch][1]);
+                for (int c = 0; c < DCT_NCH; ++c)
+                    *reinterpret_cast<uint2 *>(s_out + ((ch0 + c) * 8 + rp_i) * DCT_TILE_W + rp_blk * 8) = make_uint2(w[c][0], w[c][1]);
             }
+        }
+        }   // channel groups
+        if (do_inverse) {
             __syncwarp();
             // ---- F: YCrCb -> BGR, + pred (wrap) -----------------------------------------------------------------------
             if (g_on) {

@@ -42,6 +42,7 @@ struct vcs_ctx {
     double *d_Q = nullptr;
     int64_t launches = 0;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
+    int dct_occupancy = 1;
     size_t smem_optin = 0;
     void *dev[NUM_DEV_SLOTS] = {nullptr};
     size_t dev_cap[NUM_DEV_SLOTS] = {0};
@@ -177,7 +178,7 @@ int launch_dct(vcs_ctx *ctx, cudaStream_t st, DctArgs &a, int nP) {
     a.Q = ctx->d_Q;
     // persistent warps: 4 CTAs of 4 warps per SM, each warp walks 8x32-pixel tiles
     const long long nitems = (long long)((a.W + DCT_TILE_W - 1) / DCT_TILE_W) * (a.H / 8) * nP;
-    long long grid = (long long)ctx->sm_count * 4;
+    long long grid = (long long)ctx->sm_count * ctx->dct_occupancy;   // exactly one resident wave
     if (grid * DCT_WARPS > nitems) grid = (nitems + DCT_WARPS - 1) / DCT_WARPS;
     dct_stage_kernel<<<(unsigned)grid, DCT_THREADS, DCT_SMEM_BYTES, st>>>(a, nP);
     CK(ctx, cudaGetLastError());
@@ -357,6 +358,11 @@ int vcs_create(int device, vcs_ctx **out) {
     if (cudaMemcpyToSymbol(c_dct, C, sizeof(C)) != cudaSuccess ||
         cudaFuncSetAttribute(dct_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)DCT_SMEM_BYTES) != cudaSuccess) {
+        delete ctx;
+        return VCS_E_CUDA;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->dct_occupancy, dct_stage_kernel, DCT_THREADS,
+                                                      DCT_SMEM_BYTES) != cudaSuccess || ctx->dct_occupancy < 1) {
         delete ctx;
         return VCS_E_CUDA;
     }

@@ -1,0 +1,34 @@
+"""Times vcs_encode_clip_host (workload C2) under different GOP-chunk schedules (VCS_PIPELINE_GOPS)."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+import vcs_h264_b200 as v
+
+scheds = sys.argv[1:] or ["", "2", "1,2", "1,2,2,2,2,2,2,1,1", "1,2,4,4,3,1", "1,1,2,3,3,3,1,1", "1,3,5,5,1", "1,1,1"]
+clip = torch.from_numpy(bench.make_clip(1234)).pin_memory()
+ce = v.ClipEncoder([bench.H, bench.W], block_size=bench.BS, search="full", search_range=bench.R, gop_len=bench.GOP,
+                   qf=bench.QF, metric=0, static_thr=bench.STATIC_THR, coef_mode=v.COEF_I8_RINT)
+hout = ce.alloc_host_outputs(bench.T, want_coef=True, want_recon=False, pinned=True)
+ref = None
+for s in scheds:
+    if s:
+        os.environ["VCS_PIPELINE_GOPS"] = s
+    else:
+        os.environ.pop("VCS_PIPELINE_GOPS", None)
+    for _ in range(3):
+        ce.encode_host(clip, hout)
+    torch.cuda.synchronize()
+    n = 10
+    t0 = time.perf_counter()
+    for _ in range(n):
+        ce.encode_host(clip, hout)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / n * 1e3
+    sig = (int(hout["mv"].to(torch.int64).sum()), int(hout["coef"].to(torch.int64).abs().sum()))
+    ref = ref or sig
+    print(f"sched {s or 'default':24s} {ms:7.3f} ms  {bench.T / ms * 1e3:7.1f} fps  same={sig == ref}", flush=True)

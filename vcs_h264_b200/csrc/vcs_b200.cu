@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -715,8 +716,39 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
     // Pipeline GOP-chunk by GOP-chunk: copy-in on s_h2d, kernels on the compute stream, copy-out
     // on s_d2h; PCIe is full duplex so the three overlap.
     const int nG = (T + gop_len - 1) / gop_len;
-    int chunk_g = nG >= 8 ? (nG + 7) / 8 : 1;
-    const int nchunks = (nG + chunk_g - 1) / chunk_g;
+    // chunk boundaries in GOPs.  VCS_PIPELINE_GOPS="1,2,4" overrides the schedule (last value repeats).
+    std::vector<int> bounds(1, 0);
+    {
+        std::vector<int> sched;
+        if (const char *e = getenv("VCS_PIPELINE_GOPS")) {
+            for (const char *q = e; *q;) {
+                char *end; long v = strtol(q, &end, 10);
+                if (end == q) break;
+                if (v > 0) sched.push_back((int)v);
+                q = *end ? end + 1 : end;
+            }
+        }
+        if (sched.empty()) {
+            // default: ramp 1,1,2,3,3,...,2,1 GOPs.  The first chunk's upload and the last chunk's download are
+            // not hidden, so both are one GOP; a chunk's upload must fit under the previous chunk's kernels
+            // (upload ~0.6x the kernel time per GOP at 1080p +-16), hence the slow ramp and the cap of 3.
+            if (nG <= 5) sched.push_back(1);
+            else {
+                const int head[3] = {1, 1, 2};
+                sched.assign(head, head + 3);
+                int mid = nG - 7;
+                for (; mid >= 3; mid -= 3) sched.push_back(3);
+                if (mid > 0) sched.push_back(mid);
+                sched.push_back(2);
+                sched.push_back(1);
+            }
+        }
+        for (size_t i = 0; bounds.back() < nG; ++i) {
+            const int g = sched[i < sched.size() ? i : sched.size() - 1];
+            bounds.push_back(bounds.back() + g < nG ? bounds.back() + g : nG);
+        }
+    }
+    const int nchunks = (int)bounds.size() - 1;
     while ((int)ctx->chunk_events.size() < 2 * nchunks) {
         cudaEvent_t e;
         CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -724,7 +756,7 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
     }
     cudaStream_t sc = ctx->stream;
     for (int c = 0; c < nchunks; ++c) {
-        const int g0 = c * chunk_g, g1 = (g0 + chunk_g < nG) ? g0 + chunk_g : nG;
+        const int g0 = bounds[c], g1 = bounds[c + 1];
         const int t0 = g0 * gop_len, t1 = (g1 * gop_len < T) ? g1 * gop_len : T;
         const int p0 = vcs_num_p_frames(t0, gop_len), p1 = vcs_num_p_frames(t1, gop_len);
         CK(ctx, cudaMemcpyAsync(d_fr + fs * t0, frames + fs * t0, fs * (t1 - t0), cudaMemcpyHostToDevice,

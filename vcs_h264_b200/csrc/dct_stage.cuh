@@ -88,8 +88,15 @@ __device__ __forceinline__ void load24(const uint8_t *p, uint32_t w[6]) {
 
 __device__ __forceinline__ uint32_t byte_of(const uint32_t *w, int k) { return (w[k >> 2] >> (8 * (k & 3))) & 0xffu; }
 
+// Compile-time variants: CM = coefficient format (VCS_COEF_*), PATH = which halves run.  The quantiser sits in the
+// innermost loop, so run-time mode tests there cost more issue slots than the arithmetic they guard.
+enum { DCT_FWD = 0, DCT_FWD_INV = 1, DCT_FWD_INV_NOCOEF = 2, DCT_INV = 3 };
+
+template <int CM, int PATH>
 __global__ void __launch_bounds__(DCT_THREADS, DCT_NCH == 1 ? 6 : 4)
 dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
+    constexpr bool forward = PATH != DCT_INV, do_inverse = PATH != DCT_FWD, has_coef = PATH != DCT_FWD_INV_NOCOEF;
+    constexpr int coef_mode = CM;
     extern __shared__ __align__(16) unsigned char dct_smem[];
     double *s_q = reinterpret_cast<double *>(dct_smem);          // Q [3][64]
     double *s_rq = s_q + 192;                                    // RN(1/Q)
@@ -101,8 +108,6 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     uint8_t *s_out = reinterpret_cast<uint8_t *>(s_in8 + DCT_PLANE);              // [3][8][32] decoded YCrCb
 
     const int W = a.W, H = a.H, bs = a.bs, nbx = a.nbx, nby = a.nby;
-    const int forward = a.forward, coef_mode = a.coef_mode;
-    const bool do_inverse = a.inverse && a.recon;
     const size_t npix = (size_t)H * W;
     const int N = nbx * nby;
 
@@ -116,16 +121,19 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     __syncthreads();   // the only CTA-wide barrier
 
     const int ntx = (W + DCT_TILE_W - 1) / DCT_TILE_W, nty = H / 8;
-    const long long nitems = (long long)ntx * nty * nP;
-    const long long nwarps = (long long)gridDim.x * DCT_WARPS;
+    const unsigned tiles_per_frame = (unsigned)(ntx * nty);
+    const unsigned nitems = tiles_per_frame * (unsigned)nP;       // < 2^31 (checked on the host)
+    const unsigned nwarps = gridDim.x * DCT_WARPS;
+    const int bs_shift = (bs & (bs - 1)) == 0 ? 31 - __clz(bs) : -1;
 
     // lane roles
     const int g_r = lane >> 2, g_c = (lane & 3) * 8;        // stages A/F: 8-pixel group (row, first column)
     const int rp_i = lane & 7, rp_blk = lane >> 3;          // row passes: row i of block blk
     const int rbase0 = rp_i * DCT_RS + rp_blk * 8;          // + ch * 8 * RS
 
-    for (long long item = (long long)blockIdx.x * DCT_WARPS + warp; item < nitems; item += nwarps) {
-        const int tx = (int)(item % ntx), ty = (int)((item / ntx) % nty), p = (int)(item / ((long long)ntx * nty));
+    for (unsigned item = blockIdx.x * DCT_WARPS + warp; item < nitems; item += nwarps) {
+        const unsigned pu = item / tiles_per_frame, rem = item - pu * tiles_per_frame, tyu = rem / (unsigned)ntx;
+        const int p = (int)pu, ty = (int)tyu, tx = (int)(rem - tyu * (unsigned)ntx);
         const int x0 = tx * DCT_TILE_W, y0 = ty * 8;
         const int tw = min(DCT_TILE_W, W - x0);   // multiple of 8
         const bool g_on = g_c < tw, col_on = lane < tw, row_on = rp_blk * 8 < tw;
@@ -145,7 +153,7 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
             // prediction: motion-compensated gather from ref (motion.py:42-69) or a given pred image
             if (mv && ref) {
                 if (bs % 8 == 0) {   // the group lies inside one macroblock
-                    const int mbx = x / bs, mby = y / bs;
+                    const int mbx = bs_shift >= 0 ? x >> bs_shift : x / bs, mby = bs_shift >= 0 ? y >> bs_shift : y / bs;
                     if (mbx < nbx && mby < nby) {   // uncovered border stays 0 (motion.py:45-46)
                         const int16_t *m = mv + 2 * (mby * nbx + mbx);
                         load24(ref + ((size_t)(y + m[1]) * W + (x + m[0])) * 3, pw);
@@ -257,7 +265,7 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                             if (fabs(fabs(q0 - v) - 0.5) < 9.313225746154785e-10)   // 2^-30 of a half-integer
                                 v = rint(s[c] / Q);                        // -> the exact quotient decides
                         }
-                        if (a.coef) {
+                        if (has_coef) {
                             if (coef_mode == 2) {
                                 const uint32_t h = (uint32_t)(uint16_t)(int16_t)(int)v;
                                 if (j & 1) pk[c][j >> 1] |= h << 16; else pk[c][j >> 1] = h;
@@ -274,12 +282,12 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                         if (do_inverse) s_x[c * 8 * DCT_RS + rbase0 + j] = v * Q;   // E = blk * Q (DCTcompressor.py:86)
                     }
                 }
-                if (a.coef && coef_mode == 2) {
+                if (has_coef && coef_mode == 2) {
 #pragma unroll
                     for (int c = 0; c < DCT_NCH; ++c)
                         *reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(a.coef) + gidx0 + (ch0 + c) * npix) =
                             make_uint4(pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
-                } else if (a.coef && coef_mode == 3) {
+                } else if (has_coef && coef_mode == 3) {
 #pragma unroll
                     for (int c = 0; c < DCT_NCH; ++c)
                         *reinterpret_cast<uint2 *>(reinterpret_cast<int8_t *>(a.coef) + gidx0 + (ch0 + c) * npix) =

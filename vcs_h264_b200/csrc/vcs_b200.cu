@@ -43,7 +43,7 @@ struct vcs_ctx {
     double *d_Q = nullptr;
     int64_t launches = 0;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
-    int dct_occupancy = 1;
+    int dct_occupancy[4][4] = {{0}};   // [coef_mode][path], filled on first use
     size_t smem_optin = 0;
     void *dev[NUM_DEV_SLOTS] = {nullptr};
     size_t dev_cap[NUM_DEV_SLOTS] = {0};
@@ -176,12 +176,30 @@ int launch_dct(vcs_ctx *ctx, cudaStream_t st, DctArgs &a, int nP) {
             return fail(ctx, VCS_E_INVALID, "int8 indices are not lossless for this Q (min %g < 9): use VCS_COEF_I16_RINT", qmin);
     }
     if (nP <= 0) return VCS_OK;
+    const bool inv = a.inverse && a.recon;
+    if (!a.forward && !inv) return fail(ctx, VCS_E_INVALID, "nothing to do: no forward pass and no reconstruction");
+    if (a.forward && !inv && !a.coef) return fail(ctx, VCS_E_INVALID, "forward pass without an output");
+    if (!a.forward && !a.coef) return fail(ctx, VCS_E_INVALID, "inverse pass without coefficients");
+    const int path = !a.forward ? DCT_INV : (!inv ? DCT_FWD : (a.coef ? DCT_FWD_INV : DCT_FWD_INV_NOCOEF));
+    typedef void (*dct_fn)(const DctArgs, int);
+#define VCS_DCT_ROW(CM) {dct_stage_kernel<CM, 0>, dct_stage_kernel<CM, 1>, dct_stage_kernel<CM, 2>, dct_stage_kernel<CM, 3>}
+    static const dct_fn table[4][4] = {VCS_DCT_ROW(0), VCS_DCT_ROW(1), VCS_DCT_ROW(2), VCS_DCT_ROW(3)};
+#undef VCS_DCT_ROW
+    const dct_fn kern = table[a.coef_mode][path];
+    int &occ = ctx->dct_occupancy[a.coef_mode][path];
+    if (occ == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DCT_THREADS, DCT_SMEM_BYTES) != cudaSuccess || occ < 1) {
+            occ = 0;
+            return fail(ctx, VCS_E_CUDA, "dct_stage_kernel does not fit an SM");
+        }
+    }
     a.Q = ctx->d_Q;
     // persistent warps: 4 CTAs of 4 warps per SM, each warp walks 8x32-pixel tiles
     const long long nitems = (long long)((a.W + DCT_TILE_W - 1) / DCT_TILE_W) * (a.H / 8) * nP;
-    long long grid = (long long)ctx->sm_count * ctx->dct_occupancy;   // exactly one resident wave
+    if (nitems >= (1ll << 31)) return fail(ctx, VCS_E_INVALID, "too many 8x32 tiles in one launch (%lld)", nitems);
+    long long grid = (long long)ctx->sm_count * occ;   // exactly one resident wave
     if (grid * DCT_WARPS > nitems) grid = (nitems + DCT_WARPS - 1) / DCT_WARPS;
-    dct_stage_kernel<<<(unsigned)grid, DCT_THREADS, DCT_SMEM_BYTES, st>>>(a, nP);
+    kern<<<(unsigned)grid, DCT_THREADS, DCT_SMEM_BYTES, st>>>(a, nP);
     CK(ctx, cudaGetLastError());
     ctx->launches += 1;
     return VCS_OK;
@@ -356,14 +374,8 @@ int vcs_create(int device, vcs_ctx **out) {
     ctx->stream = ctx->own_stream;
     double C[64];
     vcs_dct_matrix(C);
-    if (cudaMemcpyToSymbol(c_dct, C, sizeof(C)) != cudaSuccess ||
-        cudaFuncSetAttribute(dct_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)DCT_SMEM_BYTES) != cudaSuccess) {
-        delete ctx;
-        return VCS_E_CUDA;
-    }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->dct_occupancy, dct_stage_kernel, DCT_THREADS,
-                                                      DCT_SMEM_BYTES) != cudaSuccess || ctx->dct_occupancy < 1) {
+    static_assert(DCT_SMEM_BYTES <= 48 * 1024, "dct_stage_kernel relies on the default shared-memory limit");
+    if (cudaMemcpyToSymbol(c_dct, C, sizeof(C)) != cudaSuccess) {
         delete ctx;
         return VCS_E_CUDA;
     }

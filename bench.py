@@ -339,7 +339,7 @@ def run_b200(args, rank, world, local_rank):
     peak_pxops = mb["vabsdiff4_acc"]["warp_instr_per_s"] * 32 * 4
 
     # DRAM bytes per launch from the ncu --set full capture of this command (profiles/r1_ncu_full_summary.csv)
-    ME_TRAFFIC, DCT_TRAFFIC = 381.6e6, 904.9e6
+    ME_TRAFFIC, DCT_TRAFFIC = 381.6e6, 1033.6e6
 
     sm_count = ctx0.device_info()["sm_count"]
 

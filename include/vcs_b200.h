@@ -201,6 +201,20 @@ int vcs_intra_chroma8x8_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Cr, const
 int vcs_intra_host(vcs_ctx *ctx, int which, int H, int W, const uint8_t *p0, const uint8_t *p1,
                    int32_t *res0, int32_t *pred0, int32_t *res1, int32_t *pred1, uint8_t *modes);
 
+/* ---- 4:2:0 chroma subsampling demo: ChromaSubsampling/chroma.py ------------------------- */
+/* chroma.py:9-21: BGR -> YCrCb, 2x2 box filter of Cr and Cb (cv2.boxFilter: anchor (1,1), reflect-101 border,
+ * ceil(sum/4)), every second sample.  Y is [H][W]; cr and cb are [ceil(H/2)][ceil(W/2)].  Any H, W >= 1. */
+int vcs_chroma420_dev(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, uint8_t *Y, uint8_t *cr, uint8_t *cb);
+/* chroma.py:27-41: the demo's float64 reconstruction to BGR [H][W][3] (as the script behaves under NumPy 2:
+ * `Cr - 128` wraps in uint8). */
+int vcs_chroma420_to_bgr_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, const uint8_t *cr, const uint8_t *cb,
+                             uint8_t *bgr);
+/* both from host buffers; bgr_out may be NULL (subsample only) */
+int vcs_chroma420_host(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, uint8_t *Y, uint8_t *cr, uint8_t *cb,
+                       uint8_t *bgr_out);
+int vcs_chroma420_to_bgr_host(vcs_ctx *ctx, int H, int W, const uint8_t *Y, const uint8_t *cr, const uint8_t *cb,
+                              uint8_t *bgr);
+
 /* ---- measurement support ------------------------------------------------------------------ */
 /* Register-only issue-rate microbenchmarks that define the INT32-pipe roofline on the box the
  * bench runs on.  which: 0 VABSDIFF4.U8.ACC, 1 IADD3, 2 LOP3, 3 IMAD, 4 IDP.4A,

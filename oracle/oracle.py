@@ -265,3 +265,28 @@ def chroma8x8(Cr, Cb):
     if rc:
         raise ValueError("chroma8x8 needs sides that are multiples of 8")
     return (*outs, modes)
+
+
+def chroma420(bgr):
+    """ChromaSubsampling/chroma.py:9-21: BGR -> [Y (H x W), crSamples, cbSamples (ceil(H/2) x ceil(W/2))]."""
+    bgr = _u8(bgr)
+    H, W, _ = bgr.shape
+    Y = np.empty((H, W), np.uint8)
+    cr = np.empty(((H + 1) // 2, (W + 1) // 2), np.uint8)
+    cb = np.empty_like(cr)
+    rc = lib().vcs_oracle_chroma420(_p(bgr, C.c_uint8), H, W, _p(Y, C.c_uint8), _p(cr, C.c_uint8), _p(cb, C.c_uint8))
+    if rc:
+        raise ValueError(f"vcs_oracle_chroma420 rc={rc}")
+    return Y, cr, cb
+
+
+def chroma420_to_bgr(Y, cr, cb):
+    """ChromaSubsampling/chroma.py:27-41 (NumPy-2 uint8 scalar wrap of `Cr - 128`, float64, truncating store)."""
+    Y, cr, cb = _plane(Y), _plane(cr), _plane(cb)
+    H, W = Y.shape
+    assert cr.shape == ((H + 1) // 2, (W + 1) // 2) == cb.shape
+    out = np.empty((H, W, 3), np.uint8)
+    rc = lib().vcs_oracle_chroma420_to_bgr(_p(Y, C.c_uint8), _p(cr, C.c_uint8), _p(cb, C.c_uint8), H, W, _p(out, C.c_uint8))
+    if rc:
+        raise ValueError(f"vcs_oracle_chroma420_to_bgr rc={rc}")
+    return out

@@ -702,3 +702,59 @@ int vcs_oracle_chroma8x8(const uint8_t *Cr, const uint8_t *Cb, int H, int W, int
         }
     return 0;
 }
+
+/* ---- 4:2:0 chroma subsampling demo (ChromaSubsampling/chroma.py) -----------------
+ * chroma.py:9        imgYYC = cv2.cvtColor(img, COLOR_BGR2YCR_CB)
+ * chroma.py:16-17    cr/cb = cv2.boxFilter(plane, ddepth=-1, ksize=(2,2))
+ *                    OpenCV 4.13: anchor = ksize/2 = (1,1), BORDER_REFLECT_101, normalised; for uint8 the
+ *                    2x2 mean comes out as ceil(sum/4) = (sum+3)>>2 (pinned for every sum 0..1020 by
+ *                    tests/golden/make_golden_chroma.py), so
+ *                    out[y][x] = (p[y-1][x-1] + p[y-1][x] + p[y][x-1] + p[y][x] + 3) >> 2, index -1 -> 1
+ * chroma.py:20-21    samples = filtered[::2, ::2]  -> ceil(H/2) x ceil(W/2)
+ * Y [H][W], crS/cbS [ceil(H/2)][ceil(W/2)]. */
+static inline int refl101(int i, int n) { return n == 1 ? 0 : (i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i)); }
+
+int vcs_oracle_chroma420(const uint8_t *bgr, int H, int W, uint8_t *Y, uint8_t *crS, uint8_t *cbS) {
+    if (H <= 0 || W <= 0) return -1;
+    const size_t npix = (size_t)H * W;
+    uint8_t *ycc = (uint8_t *)malloc(npix * 3);
+    if (!ycc) return -2;
+    vcs_oracle_bgr2ycrcb(bgr, npix, ycc);
+    for (size_t k = 0; k < npix; ++k) Y[k] = ycc[3 * k];
+    const int h2 = (H + 1) / 2, w2 = (W + 1) / 2;
+    for (int i = 0; i < h2; ++i)
+        for (int j = 0; j < w2; ++j) {
+            const int y0 = refl101(2 * i - 1, H), y1 = 2 * i, x0 = refl101(2 * j - 1, W), x1 = 2 * j;
+            for (int c = 1; c <= 2; ++c) {
+                const int s = ycc[((size_t)y0 * W + x0) * 3 + c] + ycc[((size_t)y0 * W + x1) * 3 + c] +
+                              ycc[((size_t)y1 * W + x0) * 3 + c] + ycc[((size_t)y1 * W + x1) * 3 + c];
+                (c == 1 ? crS : cbS)[(size_t)i * w2 + j] = (uint8_t)((s + 3) >> 2);
+            }
+        }
+    free(ycc);
+    return 0;
+}
+
+/* chroma.py:27-41: per pixel, with NumPy-2 scalar semantics as run in this container: Y, Cr, Cb are np.uint8
+ * scalars, so `Cr - 128` WRAPS mod 256 (uint8 - weak Python int), the products with Python floats are float64,
+ *   r = Y + 1.4022*crw;  g = (Y - 0.34414*cbw) - 0.71414*crw;  b = Y + 1.772*cbw
+ * each clamped to [0,255] and truncated by the store into the uint8 image (chroma.py:41 `[b, g, r]`). */
+int vcs_oracle_chroma420_to_bgr(const uint8_t *Y, const uint8_t *crS, const uint8_t *cbS, int H, int W, uint8_t *bgr) {
+    if (H <= 0 || W <= 0) return -1;
+    const int w2 = (W + 1) / 2;
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const double y = Y[(size_t)i * W + j];
+            const double crw = (uint8_t)(crS[(size_t)(i / 2) * w2 + j / 2] - 128);
+            const double cbw = (uint8_t)(cbS[(size_t)(i / 2) * w2 + j / 2] - 128);
+            double r = y + 1.4022 * crw;
+            double g = (y - 0.34414 * cbw) - 0.71414 * crw;
+            double b = y + 1.77200 * cbw;
+            r = r < 0 ? 0 : (r > 255 ? 255 : r);
+            g = g < 0 ? 0 : (g > 255 ? 255 : g);
+            b = b < 0 ? 0 : (b > 255 ? 255 : b);
+            uint8_t *o = bgr + ((size_t)i * W + j) * 3;
+            o[0] = (uint8_t)b; o[1] = (uint8_t)g; o[2] = (uint8_t)r;
+        }
+    return 0;
+}

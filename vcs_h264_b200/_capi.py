@@ -83,6 +83,10 @@ SIGNATURES = {
     "vcs_intra_luma16x16_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "vcs_intra_chroma8x8_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vcs_intra_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vcs_chroma420_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "vcs_chroma420_to_bgr_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "vcs_chroma420_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "vcs_chroma420_to_bgr_host": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "vcs_microbench": (_i, [_vp, _i, _i, C.POINTER(_d), C.POINTER(_d)]),
     "vcs_enable_kernel_timing": (_i, [_vp, _i]),
     "vcs_kernel_times": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), C.POINTER(_i)]),

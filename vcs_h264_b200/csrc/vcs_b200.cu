@@ -14,6 +14,7 @@
 
 #include "../../include/vcs_b200.h"
 #include "common.cuh"
+#include "chroma.cuh"
 #include "dct_stage.cuh"
 #include "intra.cuh"
 #include "me_generic.cuh"
@@ -906,6 +907,72 @@ int vcs_kernel_times(vcs_ctx *ctx, double *me_ms_total, double *dct_ms_total, in
     if (dct_ms_total) *dct_ms_total = dct;
     if (ncalls) *ncalls = (int)ctx->ev_used;
     ctx->ev_used = 0;
+    return VCS_OK;
+}
+
+// ---- 4:2:0 chroma subsampling demo (ChromaSubsampling/chroma.py) ------------------------------------
+int vcs_chroma420_dev(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, uint8_t *Y, uint8_t *cr, uint8_t *cb) {
+    if (!ctx) return VCS_E_INVALID;
+    if (H <= 0 || W <= 0 || !bgr || !Y || !cr || !cb) return fail(ctx, VCS_E_INVALID, "bad chroma420 arguments");
+    const dim3 block(32, 8), grid((W / 2 + 1 + 31) / 32, (H / 2 + 1 + 7) / 8);
+    chroma420_kernel<<<grid, block, 0, ctx->stream>>>(bgr, H, W, Y, cr, cb);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return VCS_OK;
+}
+
+int vcs_chroma420_to_bgr_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, const uint8_t *cr, const uint8_t *cb,
+                             uint8_t *bgr) {
+    if (!ctx) return VCS_E_INVALID;
+    if (H <= 0 || W <= 0 || !bgr || !Y || !cr || !cb) return fail(ctx, VCS_E_INVALID, "bad chroma420 arguments");
+    const size_t npix = (size_t)H * W;
+    size_t blocks = (npix + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    chroma420_to_bgr_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(Y, cr, cb, H, W, bgr);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return VCS_OK;
+}
+
+int vcs_chroma420_host(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, uint8_t *Y, uint8_t *cr, uint8_t *cb,
+                       uint8_t *bgr_out) {
+    if (!ctx) return VCS_E_INVALID;
+    if (H <= 0 || W <= 0 || !bgr || !Y || !cr || !cb) return fail(ctx, VCS_E_INVALID, "bad chroma420 arguments");
+    const size_t npix = (size_t)H * W, ns = (size_t)((H + 1) / 2) * ((W + 1) / 2);
+    uint8_t *d_img, *d_pl, *d_out = nullptr;
+    int rc;
+    if ((rc = dev_buf(ctx, S_FRAMES, npix * 3, (void **)&d_img))) return rc;
+    if ((rc = dev_buf(ctx, S_AUX0, npix + 2 * ns, (void **)&d_pl))) return rc;
+    if (bgr_out && (rc = dev_buf(ctx, S_RECON, npix * 3, (void **)&d_out))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(d_img, bgr, npix * 3, cudaMemcpyHostToDevice, st));
+    if ((rc = vcs_chroma420_dev(ctx, H, W, d_img, d_pl, d_pl + npix, d_pl + npix + ns))) return rc;
+    if (bgr_out && (rc = vcs_chroma420_to_bgr_dev(ctx, H, W, d_pl, d_pl + npix, d_pl + npix + ns, d_out))) return rc;
+    CK(ctx, cudaMemcpyAsync(Y, d_pl, npix, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(cr, d_pl + npix, ns, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(cb, d_pl + npix + ns, ns, cudaMemcpyDeviceToHost, st));
+    if (bgr_out) CK(ctx, cudaMemcpyAsync(bgr_out, d_out, npix * 3, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return VCS_OK;
+}
+
+int vcs_chroma420_to_bgr_host(vcs_ctx *ctx, int H, int W, const uint8_t *Y, const uint8_t *cr, const uint8_t *cb,
+                              uint8_t *bgr) {
+    if (!ctx) return VCS_E_INVALID;
+    if (H <= 0 || W <= 0 || !bgr || !Y || !cr || !cb) return fail(ctx, VCS_E_INVALID, "bad chroma420 arguments");
+    const size_t npix = (size_t)H * W, ns = (size_t)((H + 1) / 2) * ((W + 1) / 2);
+    uint8_t *d_pl, *d_out;
+    int rc;
+    if ((rc = dev_buf(ctx, S_AUX0, npix + 2 * ns, (void **)&d_pl))) return rc;
+    if ((rc = dev_buf(ctx, S_RECON, npix * 3, (void **)&d_out))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(d_pl, Y, npix, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(d_pl + npix, cr, ns, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(d_pl + npix + ns, cb, ns, cudaMemcpyHostToDevice, st));
+    if ((rc = vcs_chroma420_to_bgr_dev(ctx, H, W, d_pl, d_pl + npix, d_pl + npix + ns, d_out))) return rc;
+    CK(ctx, cudaMemcpyAsync(bgr, d_out, npix * 3, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
     return VCS_OK;
 }
 

@@ -67,8 +67,28 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         intra[name + "_ms"] = e0.elapsed_time(e1) / 10
+    # 4:2:0 chroma subsampling of the same still (ChromaSubsampling/chroma.py:9-41), device resident
+    h2, w2 = (H + 1) // 2, (W + 1) // 2
+    Yp = torch.empty((H, W), dtype=torch.uint8, device="cuda")
+    crs, cbs = (torch.empty((h2, w2), dtype=torch.uint8, device="cuda") for _ in range(2))
+    back = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+    chroma = {}
+    for name, fn, nbytes in (("subsample", lambda: ctx.call("vcs_chroma420_dev", H, W, _capi.ptr(stills[0]), _capi.ptr(Yp), _capi.ptr(crs), _capi.ptr(cbs)), H * W * 4 + 2 * h2 * w2),
+                             ("to_bgr", lambda: ctx.call("vcs_chroma420_to_bgr_dev", H, W, _capi.ptr(Yp), _capi.ptr(crs), _capi.ptr(cbs), _capi.ptr(back)), H * W * 4 + 2 * h2 * w2)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        chroma[name + "_ms"] = ms
+        chroma[name + "_GBps"] = nbytes / (ms * 1e-3) / 1e9
     print(json.dumps({"workload": "synthetic 2160x3840 stills, 8x8 DCT f64, rint quantiser -> int16", "rows": rows,
-                      "intra_4k": intra}))
+                      "intra_4k": intra, "chroma420_4k": chroma}))
 
 
 if __name__ == "__main__":

@@ -345,3 +345,24 @@ def test_main_driver_frame_and_clip_modes_agree(vcs, orc):
     for t in range(7):
         want = frames[t] if t % 4 == 0 else orc.encode_p(frames[t], frames[(t // 4) * 4], 8, **prm)["recon"]
         assert np.array_equal(dec_f[t], want) and np.array_equal(dec_c[t], want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("qf", [50, 25, 10])
+def test_quantiser_exact_half_integers(vcs, orc, qf):
+    """Flat 8x8 blocks give D[0][0] = 8*(v-128): with even Q entries the quotient is an exact half-integer for
+    many grey levels, where the kernel's q0 = D*RN(1/Q) shortcut must hand over to the IEEE quotient and
+    np.round's half-to-even (dct.py:179) decides.  Gradients add near-ties on the AC terms."""
+    H, W = 128, 256
+    rng = np.random.default_rng(qf)
+    grey = np.repeat(np.repeat(rng.integers(0, 256, (H // 8, W // 8), dtype=np.uint8), 8, 0), 8, 1)
+    img = np.stack([grey, grey, grey], -1)                     # B = G = R -> Y = grey, Cr = Cb = 128
+    img[64:] = np.clip(img[64:].astype(int) + (np.arange(W)[None, :, None] % 8) * 2, 0, 255).astype(np.uint8)
+    dc = vcs.DCTCompressor(8)
+    dc.Q = list(orc.qtables(float(qf)))
+    got = np.stack(dc.compress(img, rounded=True))
+    want = orc.compress(img, Q=orc.qtables(float(qf)), round_mode=1)
+    assert np.array_equal(got, want)
+    halves = np.abs(np.abs(orc.compress(img, Q=orc.qtables(float(qf)), round_mode=0)) % 1.0 - 0.5) < 1e-12
+    assert halves.sum() > 50                                    # the case under test really occurs
+    assert np.array_equal(dc.compress_indices(img), want.astype(np.int16))

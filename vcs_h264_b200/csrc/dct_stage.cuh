@@ -239,59 +239,69 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                 for (int c = 0; c < DCT_NCH; ++c)
 #pragma unroll
                     for (int k = 0; k < 8; ++k) tk[c][k] = s_x[c * 8 * DCT_RS + rbase0 + k];
-                uint32_t pk[DCT_NCH][4];
-                double dprev[DCT_NCH];
+                // All 8 chains first (one basic block: the DFMAs of different j interleave), then the quantiser.
+                // The rounded modes take q0 = D * RN(1/Q); a lane whose q0 comes within 2^-30 of a half-integer
+                // (|q0 - rint(q0)| > 0.5 - 2^-30) is re-done with the IEEE quotient in a rarely taken second pass.
+                constexpr double NEAR_HALF = 0.5 - 9.313225746154785e-10;
+                double sj[DCT_NCH][8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    double s[DCT_NCH];
 #pragma unroll
-                    for (int c = 0; c < DCT_NCH; ++c) s[c] = 0.0;
+                    for (int c = 0; c < DCT_NCH; ++c) sj[c][j] = 0.0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const double cc = c_dct[j * 8 + k];
 #pragma unroll
-                        for (int c = 0; c < DCT_NCH; ++c) s[c] = __fma_rn(tk[c][k], cc, s[c]);
-                    }
-#pragma unroll
-                    for (int c = 0; c < DCT_NCH; ++c) {
-                        const int ch = ch0 + c;
-                        const double Q = s_q[ch * 64 + j * 8 + rp_i];
-                        double v;
-                        if (coef_mode == 0) {
-                            v = s[c] / Q;                                  // np.true_divide (DCTcompressor.py:71)
-                        } else {
-                            const double q0 = s[c] * s_rq[ch * 64 + j * 8 + rp_i];
-                            v = rint(q0);                                  // np.round (dct.py:179) of RN(s/Q):
-                            if (fabs(fabs(q0 - v) - 0.5) < 9.313225746154785e-10)   // 2^-30 of a half-integer
-                                v = rint(s[c] / Q);                        // -> the exact quotient decides
-                        }
-                        if (has_coef) {
-                            if (coef_mode == 2) {
-                                const uint32_t h = (uint32_t)(uint16_t)(int16_t)(int)v;
-                                if (j & 1) pk[c][j >> 1] |= h << 16; else pk[c][j >> 1] = h;
-                            } else if (coef_mode == 3) {   // int8: lossless when 1024 / min(Q) <= 127 (checked on the host)
-                                const uint32_t h = (uint32_t)(uint8_t)(int8_t)(int)v;
-                                if (j & 3) pk[c][j >> 2] |= h << (8 * (j & 3)); else pk[c][j >> 2] = h;
-                            } else if (j & 1) {
-                                *reinterpret_cast<double2 *>(reinterpret_cast<double *>(a.coef) + gidx0 + ch * npix + j - 1) =
-                                    make_double2(dprev[c], v);
-                            } else {
-                                dprev[c] = v;
-                            }
-                        }
-                        if (do_inverse) s_x[c * 8 * DCT_RS + rbase0 + j] = v * Q;   // E = blk * Q (DCTcompressor.py:86)
+                        for (int c = 0; c < DCT_NCH; ++c) sj[c][j] = __fma_rn(tk[c][k], cc, sj[c][j]);
                     }
                 }
-                if (has_coef && coef_mode == 2) {
 #pragma unroll
-                    for (int c = 0; c < DCT_NCH; ++c)
-                        *reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(a.coef) + gidx0 + (ch0 + c) * npix) =
-                            make_uint4(pk[c][0], pk[c][1], pk[c][2], pk[c][3]);
-                } else if (has_coef && coef_mode == 3) {
+                for (int c = 0; c < DCT_NCH; ++c) {
+                    const int ch = ch0 + c;
+                    bool exact = coef_mode == 0;        // un-rounded mode: np.true_divide (DCTcompressor.py:71)
+#pragma unroll 1
+                    for (int attempt = 0; attempt < 2; ++attempt) {
+                        bool near_half = false;
+                        uint32_t pk[4];
+                        double dprev = 0.0;
 #pragma unroll
-                    for (int c = 0; c < DCT_NCH; ++c)
-                        *reinterpret_cast<uint2 *>(reinterpret_cast<int8_t *>(a.coef) + gidx0 + (ch0 + c) * npix) =
-                            make_uint2(pk[c][0], pk[c][1]);
+                        for (int j = 0; j < 8; ++j) {
+                            const double Q = s_q[ch * 64 + j * 8 + rp_i];
+                            double v;
+                            if (coef_mode == 0) {
+                                v = sj[c][j] / Q;
+                            } else if (!exact) {
+                                const double q0 = sj[c][j] * s_rq[ch * 64 + j * 8 + rp_i];
+                                v = rint(q0);                              // np.round (dct.py:179) of RN(s/Q)
+                                near_half |= fabs(q0 - v) > NEAR_HALF;
+                            } else {
+                                v = rint(sj[c][j] / Q);                    // the exact quotient decides
+                            }
+                            if (has_coef) {
+                                if (coef_mode == 2) {
+                                    const uint32_t h = (uint32_t)(uint16_t)(int16_t)(int)v;
+                                    if (j & 1) pk[j >> 1] |= h << 16; else pk[j >> 1] = h;
+                                } else if (coef_mode == 3) {   // int8: lossless when 1024 / min(Q) <= 127 (checked on the host)
+                                    const uint32_t h = (uint32_t)(uint8_t)(int8_t)(int)v;
+                                    if (j & 3) pk[j >> 2] |= h << (8 * (j & 3)); else pk[j >> 2] = h;
+                                } else if (j & 1) {
+                                    *reinterpret_cast<double2 *>(reinterpret_cast<double *>(a.coef) + gidx0 + ch * npix + j - 1) =
+                                        make_double2(dprev, v);
+                                } else {
+                                    dprev = v;
+                                }
+                            }
+                            if (do_inverse) s_x[c * 8 * DCT_RS + rbase0 + j] = v * Q;   // E = blk * Q (DCTcompressor.py:86)
+                        }
+                        if (has_coef && coef_mode == 2)
+                            *reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(a.coef) + gidx0 + ch * npix) =
+                                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        else if (has_coef && coef_mode == 3)
+                            *reinterpret_cast<uint2 *>(reinterpret_cast<int8_t *>(a.coef) + gidx0 + ch * npix) =
+                                make_uint2(pk[0], pk[1]);
+                        if (exact || !near_half) break;   // per lane; the second attempt redoes this lane's row exactly
+                        exact = true;
+                    }
                 }
             }
         } else if (do_inverse && row_on) {

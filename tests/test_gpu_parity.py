@@ -366,3 +366,45 @@ def test_quantiser_exact_half_integers(vcs, orc, qf):
     halves = np.abs(np.abs(orc.compress(img, Q=orc.qtables(float(qf)), round_mode=0)) % 1.0 - 0.5) < 1e-12
     assert halves.sum() > 50                                    # the case under test really occurs
     assert np.array_equal(dc.compress_indices(img), want.astype(np.int16))
+
+
+@pytest.mark.gpu
+def test_full_size_properties_4k_range32(vcs, orc):
+    """BASELINE config 3 geometry (2160x3840, bs 16, +/-32 = 4 chunks of the 65x65 offset range per tile):
+    (i) a planted shift beyond +/-16 is found exactly (SAD, zero cost away from the borders);
+    (ii) top, middle-free and bottom strips agree bit-exactly with the oracle under the reference cost
+         with the static test on (wrap8, thr 2000), including the clipped candidate sets at the borders."""
+    from vcs_h264_b200 import synth
+    H, W, bs, R = 2160, 3840, 16, 32
+    base = synth.texture(H, W, seed=11, margin=64)
+    ref = np.ascontiguousarray(base[64:64 + H, 64:64 + W])
+    cur = np.ascontiguousarray(base[64 - 27:64 - 27 + H, 64 + 30:64 + 30 + W])      # cur(y,x) = ref(y-27, x+30)
+    ce = vcs.ClipEncoder([H, W], block_size=bs, search="full", search_range=R, gop_len=2,
+                         metric=vcs.METRIC_SAD, static_thr=-1, coef_mode=2)
+    out = ce.encode_host(np.stack([ref, cur]), want_coef=False, want_recon=False)
+    nby, nbx = H // bs, W // bs
+    mv = np.asarray(out["mv"][0]).astype(np.int32).reshape(nby, nbx, 2)
+    cost = np.asarray(out["cost"][0]).view(np.uint32).reshape(nby, nbx)
+    inner = (slice(2, None), slice(0, nbx - 2))
+    assert np.all(mv[inner] == [30, -27]) and np.all(cost[inner] == 0)
+    # (ii) strips: the first 3 MB rows only see reference rows < 3*16+32; same for the last 3 by symmetry
+    rng = np.random.default_rng(5)
+    cur2 = np.clip(cur.astype(np.int16) + rng.integers(-2, 3, cur.shape), 0, 255).astype(np.uint8)
+    cur2[:16, :64] = ref[:16, :64]                                                   # a few static blocks
+    ce2 = vcs.ClipEncoder([H, W], block_size=bs, search="full", search_range=R, gop_len=2, coef_mode=2)
+    out2 = ce2.encode_host(np.stack([ref, cur2]), want_coef=False, want_recon=False)
+    mv2 = np.asarray(out2["mv"][0]).astype(np.int32).reshape(nby, nbx, 2)
+    cost2 = np.asarray(out2["cost"][0]).view(np.uint32).reshape(nby, nbx)
+    fl2 = np.asarray(out2["flags"][0]).reshape(nby, nbx)
+    rows, need = 3, 3 * bs + R
+    top = orc.me(cur2[:need], ref[:need], bs, **orc.symmetric_search_params(R))
+    bot = orc.me(cur2[H - need:], ref[H - need:], bs, **orc.symmetric_search_params(R))
+    nb_strip = need // bs
+    for got_rows, o, sl in ((slice(0, rows), top, slice(0, rows)), (slice(nby - rows, nby), bot, slice(nb_strip - rows, nb_strip))):
+        omv = o[0].reshape(nb_strip, nbx, 2)[sl]
+        ocost = o[1].reshape(nb_strip, nbx)[sl]
+        ofl = o[2].reshape(nb_strip, nbx)[sl]
+        assert np.array_equal(mv2[got_rows], omv)
+        assert np.array_equal(fl2[got_rows], ofl)
+        assert np.array_equal(cost2[got_rows][ofl == 0], ocost[ofl == 0])
+    assert fl2[0, :4].all()                                                          # the planted static blocks

@@ -1,4 +1,4 @@
-"""Times vcs_encode_clip_host (workload C2) under different GOP-chunk schedules (VCS_PIPELINE_GOPS)."""
+"""Times vcs_encode_clip_host (workload C2) under different GOP-chunk schedules (VCS_PIPELINE_P)."""
 import os
 import sys
 import time
@@ -9,7 +9,7 @@ import torch
 import bench
 import vcs_h264_b200 as v
 
-scheds = sys.argv[1:] or ["", "2", "1,2", "1,2,2,2,2,2,2,1,1", "1,2,4,4,3,1", "1,1,2,3,3,3,1,1", "1,3,5,5,1", "1,1,1"]
+scheds = sys.argv[1:] or ["", "3", "6", "1,2,3,4,6,8,8,8,4,1", "1,2,4,6,8,8,9,4,2,1", "1,1,2,3,4,6,8,8,8,3,1", "1,2,4,4,8,8,8,4,4,2", "1,3,4,8,8,8,8,4,1", ""]
 clip = torch.from_numpy(bench.make_clip(1234)).pin_memory()
 ce = v.ClipEncoder([bench.H, bench.W], block_size=bench.BS, search="full", search_range=bench.R, gop_len=bench.GOP,
                    qf=bench.QF, metric=0, static_thr=bench.STATIC_THR, coef_mode=v.COEF_I8_RINT)
@@ -17,9 +17,9 @@ hout = ce.alloc_host_outputs(bench.T, want_coef=True, want_recon=False, pinned=T
 ref = None
 for s in scheds:
     if s:
-        os.environ["VCS_PIPELINE_GOPS"] = s
+        os.environ["VCS_PIPELINE_P"] = s
     else:
-        os.environ.pop("VCS_PIPELINE_GOPS", None)
+        os.environ.pop("VCS_PIPELINE_P", None)
     for _ in range(3):
         ce.encode_host(clip, hout)
     torch.cuda.synchronize()

@@ -14,15 +14,17 @@ struct FrameAddr {
     const uint8_t *cur_base;
     const uint8_t *ref_base;
     long long cur_gop_stride, cur_frame_stride, ref_gop_stride;
-    int ppg;  // P-frames per GOP
+    int ppg;        // P-frames per GOP
+    int p_off = 0;  // P-ordinal of launch-local p = 0 relative to cur_base / ref_base (launches that start inside a GOP)
 };
 
 __device__ __forceinline__ const uint8_t *cur_frame(const FrameAddr &a, int p) {
+    p += a.p_off;
     return a.cur_base + (long long)(p / a.ppg) * a.cur_gop_stride +
            (long long)(p % a.ppg) * a.cur_frame_stride;
 }
 __device__ __forceinline__ const uint8_t *ref_frame(const FrameAddr &a, int p) {
-    return a.ref_base + (long long)(p / a.ppg) * a.ref_gop_stride;
+    return a.ref_base + (long long)((p + a.p_off) / a.ppg) * a.ref_gop_stride;
 }
 
 // Search geometry shared by both ME kernels (include/vcs_b200.h: vcs_me_params).

@@ -78,7 +78,7 @@ struct TiledArgs {
     int tiles_x, tiles_y;      // tiles per frame
     int ncy, ncx;              // chunks of the offset range per axis
     int zchunk;                // index (cy*ncx+cx) of the chunk holding offset (0,0), or 0
-    int npairs, ppg;
+    int npairs, ppg, p_off;
     uint32_t zero;             // always 0; opaque to the compiler (pipe balancing, see the wrap8 loop)
     int16_t *mv;
     uint32_t *cost;
@@ -173,10 +173,11 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
         const int xw0 = tx * MX * BS + a.lo + cx * ND, yw0 = ty * C::MY * BS + a.lo + cy * ND;
         mbar_expect_tx(&sBar[b], (uint32_t)(C::RAWW * C::WR * 4 + C::CURW * C::CURR * 4));
         // the innermost TMA coordinate must land on a 16-byte boundary: align down, keep the remainder
+        const int pg = p + a.p_off;   // launches may start inside a GOP
         tma_load_3d(smem + C::OFF_RAW + b * C::SZ_RAW_AL, &tm_ref, &sBar[b], 4 * floordiv16(3 * xw0), yw0,
-                    p / a.ppg);
+                    pg / a.ppg);
         tma_load_4d(smem + C::OFF_CRAW + b * C::SZ_CRAW_AL, &tm_cur, &sBar[b], 4 * floordiv16(tx * MX * BS * 3),
-                    ty * C::MY * BS, p % a.ppg, p / a.ppg);
+                    ty * C::MY * BS, pg % a.ppg, pg / a.ppg);
     };
 
     if (tid == 0) {
@@ -427,7 +428,7 @@ int me_tiled_run(MeTiledState &st, cudaStream_t stream, const MeGeom &g, const F
     }
     const int pitch = 3 * g.W;
     const long long fs = (long long)pitch * g.H;
-    const int nG = (npairs + fa.ppg - 1) / fa.ppg;
+    const int nG = (fa.p_off + npairs + fa.ppg - 1) / fa.ppg;
     // reference frames: words x rows x gop
     CUtensorMap tm_ref, tm_cur;
     {
@@ -459,7 +460,7 @@ int me_tiled_run(MeTiledState &st, cudaStream_t stream, const MeGeom &g, const F
     a.ncy = a.ncx = (nd_total + C::ND - 1) / C::ND;
     a.zchunk = 0;
     if (g.lo <= 0 && g.hi >= 0) { const int cz = (-g.lo) / C::ND; a.zchunk = cz * a.ncx + cz; }
-    a.npairs = npairs; a.ppg = fa.ppg; a.zero = 0; a.mv = mv; a.cost = cost; a.flags = flags;
+    a.npairs = npairs; a.ppg = fa.ppg; a.p_off = fa.p_off; a.zero = 0; a.mv = mv; a.cost = cost; a.flags = flags;
     const long long ntiles = (long long)a.tiles_x * a.tiles_y * npairs;
     long long grid = (long long)sm_count * st.occupancy[bi][ni][METRIC];
     if (grid > ntiles) grid = ntiles;

@@ -726,14 +726,18 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
     if (coef && (rc = dev_buf(ctx, S_COEF, (size_t)nP * npix * 3 * ce + 8, &d_coef))) return rc;
     if (recon && (rc = dev_buf(ctx, S_RECON, (size_t)nP * fs + 4, (void **)&d_rec))) return rc;
 
-    // Pipeline GOP-chunk by GOP-chunk: copy-in on s_h2d, kernels on the compute stream, copy-out
-    // on s_d2h; PCIe is full duplex so the three overlap.
-    const int nG = (T + gop_len - 1) / gop_len;
-    // chunk boundaries in GOPs.  VCS_PIPELINE_GOPS="1,2,4" overrides the schedule (last value repeats).
-    std::vector<int> bounds(1, 0);
+    // Pipeline: copy-in on s_h2d, kernels on the compute stream, copy-out on s_d2h, chained with events; PCIe
+    // is full duplex so the three overlap.  Segments are ranges of P-frames (they may start and end inside a GOP):
+    // only the first upload and the last download are exposed, so the schedule starts and ends with one P-frame
+    // and ramps in between (a segment's upload has to fit under the previous segment's kernels).  A search
+    // launch wastes its last partial wave of tiles (every CTA owns an SM for ~55 us per tile at 1080p), so each
+    // size is nudged by +-1 towards a whole number of waves.  VCS_PIPELINE_P="1,2,4,8" overrides the sizes (the
+    // last value repeats).
+    const int ppg = gop_len - 1;
+    std::vector<int> sizes;
     {
         std::vector<int> sched;
-        if (const char *e = getenv("VCS_PIPELINE_GOPS")) {
+        if (const char *e = getenv("VCS_PIPELINE_P")) {
             for (const char *q = e; *q;) {
                 char *end; long v = strtol(q, &end, 10);
                 if (end == q) break;
@@ -741,44 +745,61 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
                 q = *end ? end + 1 : end;
             }
         }
-        if (sched.empty()) {
-            // default: ramp 1,1,2,3,3,...,2,1 GOPs.  The first chunk's upload and the last chunk's download are
-            // not hidden, so both are one GOP; a chunk's upload must fit under the previous chunk's kernels
-            // (upload ~0.6x the kernel time per GOP at 1080p +-16), hence the slow ramp and the cap of 3.
-            if (nG <= 5) sched.push_back(1);
-            else {
-                const int head[3] = {1, 1, 2};
-                sched.assign(head, head + 3);
-                int mid = nG - 7;
-                for (; mid >= 3; mid -= 3) sched.push_back(3);
-                if (mid > 0) sched.push_back(mid);
-                sched.push_back(2);
-                sched.push_back(1);
+        if (!sched.empty()) {
+            for (size_t i = 0, left = (size_t)nP; left > 0; ++i) {
+                size_t n = (size_t)sched[i < sched.size() ? i : sched.size() - 1];
+                if (n > left) n = left;
+                sizes.push_back((int)n);
+                left -= n;
             }
-        }
-        for (size_t i = 0; bounds.back() < nG; ++i) {
-            const int g = sched[i < sched.size() ? i : sched.size() - 1];
-            bounds.push_back(bounds.back() + g < nG ? bounds.back() + g : nG);
+        } else {
+            const double waves1 = (double)(((p->W / p->bs) + 4) / 5) * (((p->H / p->bs) + 2) / 3) / ctx->sm_count;
+            auto waste = [&](int n) { const double w = n * waves1; return (ceil(w - 1e-9) - w) / w; };
+            auto nudge = [&](int n, int cap) {          // n-1, n or n+1, whichever wastes least of its last wave
+                int best = n;
+                for (int c = n - 1; c <= n + 1; c += 2)
+                    if (c >= 1 && c <= cap && waste(c) < waste(best) - 1e-9) best = c;
+                return best;
+            };
+            const int head[5] = {1, 2, 3, 4, 6}, tail[3] = {4, 2, 1};
+            int left = nP, tail_sum = 0;
+            std::vector<int> back;
+            if (nP >= 12) for (int k = 2; k >= 0; --k) { back.push_back(tail[k]); tail_sum += tail[k]; }   // 1, 2, 4
+            left -= tail_sum;
+            for (int k = 0; left > 0; ++k) {
+                int n = k < 5 ? head[k] : 8;
+                if (n > left) n = left; else if (k > 0) { n = nudge(n, left); }
+                sizes.push_back(n);
+                left -= n;
+            }
+            for (size_t k = back.size(); k-- > 0;) sizes.push_back(back[k]);
         }
     }
-    const int nchunks = (int)bounds.size() - 1;
-    while ((int)ctx->chunk_events.size() < 2 * nchunks) {
+    const int nsegs = (int)sizes.size();
+    while ((int)ctx->chunk_events.size() < 2 * nsegs) {
         cudaEvent_t e;
         CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->chunk_events.push_back(e);
     }
+    // (Running consecutive searches on two streams so that one fills the other's tail was tried and is slower:
+    // the persistent search CTAs of the next chunk then keep the DCT stage of this chunk off the SMs.)
     cudaStream_t sc = ctx->stream;
-    for (int c = 0; c < nchunks; ++c) {
-        const int g0 = bounds[c], g1 = bounds[c + 1];
-        const int t0 = g0 * gop_len, t1 = (g1 * gop_len < T) ? g1 * gop_len : T;
-        const int p0 = vcs_num_p_frames(t0, gop_len), p1 = vcs_num_p_frames(t1, gop_len);
-        CK(ctx, cudaMemcpyAsync(d_fr + fs * t0, frames + fs * t0, fs * (t1 - t0), cudaMemcpyHostToDevice,
-                                ctx->s_h2d));
-        CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c], ctx->s_h2d));
-        CK(ctx, cudaStreamWaitEvent(sc, ctx->chunk_events[2 * c], 0));
-        const int np = p1 - p0;
-        if (np > 0) {
-            FrameAddr fa = clip_addr(d_fr + fs * t0, p->H, p->W, gop_len);
+    int uploaded = 0, p0 = 0;
+    for (int c = 0; c < nsegs; ++c) {                    // frames after the last P-frame are never needed on the device
+        const int np = sizes[c];
+        const int plast = p0 + np - 1;
+        const int t_need = (plast / ppg) * gop_len + 1 + plast % ppg + 1;   // frames [0, t_need) must be resident
+        if (t_need > uploaded) {
+            CK(ctx, cudaMemcpyAsync(d_fr + fs * uploaded, frames + fs * uploaded, fs * (t_need - uploaded),
+                                    cudaMemcpyHostToDevice, ctx->s_h2d));
+            CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c], ctx->s_h2d));
+            CK(ctx, cudaStreamWaitEvent(sc, ctx->chunk_events[2 * c], 0));
+            uploaded = t_need;
+        }
+        {
+            const int g0 = p0 / ppg;
+            FrameAddr fa = clip_addr(d_fr + fs * (size_t)g0 * gop_len, p->H, p->W, gop_len);
+            fa.p_off = p0 - g0 * ppg;
             rc = encode_dev(ctx, sc, p, fa, np, coef_mode, d_mv + (size_t)p0 * N * 2, d_cost + (size_t)p0 * N,
                             d_fl + (size_t)p0 * N,
                             d_coef ? (void *)((char *)d_coef + (size_t)p0 * npix * 3 * ce) : nullptr,
@@ -800,6 +821,7 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
             if (recon) CK(ctx, cudaMemcpyAsync(recon + (size_t)p0 * fs, d_rec + (size_t)p0 * fs, (size_t)np * fs,
                                                cudaMemcpyDeviceToHost, ctx->s_d2h));
         }
+        p0 += np;
     }
     CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
     CK(ctx, cudaStreamSynchronize(sc));

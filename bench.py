@@ -163,14 +163,14 @@ def run_reference(args, rank, world):
     fps = sample_frames * args.steps / dt
     sample = (f"the whole {sample_frames}-frame clip ({sample_frames // GOP} I + "
               f"{sample_frames - sample_frames // GOP} P) per step, C port with SSE2 costs + OpenMP over macroblocks")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC_NAME, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
         "data": "synthetic", "config": workload_config(),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def workload_config():
@@ -382,12 +382,27 @@ def run_b200(args, rank, world, local_rank):
     if world == 1 and not args.skip_cpu:
         line["cpu_baseline"] = cpu_baseline_sample()
         line["parity_check"] = parity_spot_check(clip_np, wrap["first_p"])
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; fd 1 itself is pointed at stderr for the whole run
+    (main()) so that library chatter -- NCCL's version banner, OpenMP notices -- can never land in front of it."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -101,9 +101,12 @@ def load():
     if _lib is not None:
         return _lib
     from . import build as _build
-    if not os.path.exists(LIB_PATH) or (_build.stale() and os.path.exists(_build.NVCC)):
-        _build.build()                   # in-tree, next to this file; raises if nvcc fails
-    lib = C.CDLL(LIB_PATH)
+    path = os.environ.get("VCS_B200_LIB")   # A/B builds of the same sources (tools/ab_me.sh); normally unset
+    if not path:
+        path = LIB_PATH
+        if not os.path.exists(LIB_PATH) or (_build.stale() and os.path.exists(_build.NVCC)):
+            _build.build()               # in-tree, next to this file; raises if nvcc fails
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError = header/library mismatch: be loud
         fn.restype = res

@@ -29,6 +29,13 @@
 
 #include "common.cuh"
 
+// wrap8 loop: VCS_WRAP_ALU_NUM of every VCS_WRAP_ALU_DEN subtracts are forced onto the ALU pipe (IADD3), the rest
+// go to the FMA pipe (IMAD.IADD); 2 of 5 measured best (tools/ab_me.sh builds and times other splits).
+#ifndef VCS_WRAP_ALU_NUM
+#define VCS_WRAP_ALU_NUM 2
+#define VCS_WRAP_ALU_DEN 5
+#endif
+
 namespace vcs {
 
 // ---- compile-time configuration of one kernel variant -------------------------------------
@@ -338,7 +345,7 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
                                         // FMA); ptxas sends them all to FMA, where IDP.4A also lives.  A third
                                         // (opaque zero) addend forces IADD3 for 2 of 5 so both pipes fill up.
                                         uint32_t z;
-                                        if (d % 5 < 2)
+                                        if (d % VCS_WRAP_ALU_DEN < VCS_WRAP_ALU_NUM)
                                             asm("{\n.reg .u32 t;\nsub.u32 t, %1, %2;\nadd.u32 t, t, %5;\n"
                                                 "lop3.b32 %0, t, %3, %4, 0x96;\n}"
                                                 : "=r"(z) : "r"(r1), "r"(c[v]), "r"(r2), "r"(chh[v]), "r"(zero));

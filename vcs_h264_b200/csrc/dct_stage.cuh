@@ -20,19 +20,21 @@
 // are always in different stages and hide each other's latencies:
 //   A  lane = one 8-pixel group: cur (3 x LDG.64) and the motion-compensated prediction (aligned
 //      words + funnel shift), residual, BGR->YCrCb-128 packed as int8 into shared memory;
-//   B  lane = one pixel column of all 3 channels: 24 inputs in registers, 8 x 3 DFMA chains, every
-//      DCT-matrix constant fetched once for the 3 channels; results in place (doubles, row stride 33);
-//   C  lane = (block, row) of all 3 channels: row pass, quantise, coefficients straight to global
-//      memory (8 int16 = one STG.128 per channel), E = q*Q back in place;
+//   then, one channel at a time (DCT_NCH = 1; the loop is not unrolled, which keeps the kernel at 58-64
+//   registers = 8 CTAs of 4 warps per SM and a third of the code):
+//   B  lane = one pixel column: 8 inputs in registers, 8 DFMA chains, results in place (doubles, row stride 33);
+//   C  lane = (block, row): row pass (all 8 chains first), quantise, coefficients straight to global
+//      memory (8 int8 / int16 = one STG.64 / STG.128), E = q*Q back in place;
 //   D/E the inverse column and row passes the same way, truncating store into packed bytes;
 //   F  lane = one 8-pixel group: YCrCb->BGR, + prediction, 3 x STG.64.
-// The kernel moves 15 B/px (int16 indices) but is FP64-pipe bound first: 96 DFMA per pixel.
+// The kernel moves 12 / 15 / 33 B/px (int8 / int16 / float64 coefficients) but is bound by instruction issue
+// and the FP64 pipe first: 96 DFMA per pixel plus one constant fetch per two of them.
 //
 // Quantiser: the reference computes rint(RN(D/Q)).  For the rounded modes the kernel takes
 // q0 = D * RN(1/Q) (within 2^-40 of the true quotient for |q| < 2^11) and only when q0 lies within
-// 2^-30 of a half-integer falls back to the IEEE divide, so the result is bit-identical while the
-// common path costs a DMUL.  The un-rounded mode (the reference's inter path, DCTcompressor.py:71)
-// always uses the IEEE divide.
+// 2^-30 of a half-integer re-does that lane's row with the IEEE divide, so the result is bit-identical
+// while the common path costs a DMUL.  The un-rounded mode (the reference's inter path,
+// DCTcompressor.py:71) always uses the IEEE divide.
 #pragma once
 #include "common.cuh"
 

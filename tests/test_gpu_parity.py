@@ -408,3 +408,28 @@ def test_full_size_properties_4k_range32(vcs, orc):
         assert np.array_equal(fl2[got_rows], ofl)
         assert np.array_equal(cost2[got_rows][ofl == 0], ocost[ofl == 0])
     assert fl2[0, :4].all()                                                          # the planted static blocks
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sched", ["", "1", "2", "5", "1,3,2", "100"])
+@pytest.mark.parametrize("geom", [(64, 96, 16, 8, 4), (40, 56, 8, 8, 4), (48, 72, 8, 4, 3), (64, 96, 16, 8, 2)])
+def test_host_pipeline_segments_equal_device(vcs, monkeypatch, sched, geom):
+    """vcs_encode_clip_host cuts the clip into P-frame segments that may start inside a GOP (FrameAddr.p_off);
+    every schedule must give the one-launch device result, for the tiled kernel (W % 16 == 0) and the generic one,
+    partial trailing GOPs and 1-P GOPs included."""
+    import torch
+    from vcs_h264_b200 import synth
+    H, W, bs, R, gop = geom
+    T = 11
+    clip = synth.clip(T, H, W, seed=H + W, margin=32)
+    if sched:
+        monkeypatch.setenv("VCS_PIPELINE_P", sched)
+    else:
+        monkeypatch.delenv("VCS_PIPELINE_P", raising=False)
+    ce = vcs.ClipEncoder([H, W], block_size=bs, search="full", search_range=R, gop_len=gop, coef_mode=2)
+    out = ce.encode_host(clip, want_coef=True, want_recon=True)
+    dout = ce.alloc_device_outputs(T)
+    ce.encode_device(torch.from_numpy(clip).cuda(), dout)
+    torch.cuda.synchronize()
+    for k in ("mv", "cost", "flags", "coef", "recon"):
+        assert torch.equal(torch.as_tensor(np.asarray(out[k])), dout[k].cpu()), k

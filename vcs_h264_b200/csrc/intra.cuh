@@ -224,17 +224,34 @@ __global__ void intra_chroma8x8_kernel(const uint8_t *__restrict__ Cr, const uin
     const int j = jm * 8, r = lane >> 2, c0 = (lane & 3) * 2;
     const bool s_l = jm > 0;
     int prev_b0 = 0, prev_b1 = 0;   // this lane's Cb residuals of the block above (rows r, cols c0, c0+1)
+    // Only the Cb up-neighbours chain from block to block; every load is independent of the chain, so the pixels of
+    // block im + 1 are fetched while block im is decided (the walk is latency bound: one warp per column).
+    struct Px { int yr0, yr1, yb0, yb1, ur0, ur1, lr, lb; };
+    auto fetch = [&](int im) {
+        Px q;
+        const int i = im * 8;
+        const size_t o = (size_t)(i + r) * W + j + c0;
+        q.yr0 = Cr[o]; q.yr1 = Cr[o + 1]; q.yb0 = Cb[o]; q.yb1 = Cb[o + 1];
+        q.ur0 = im > 0 ? Cr[(size_t)(i - 1) * W + j + c0] : 128;
+        q.ur1 = im > 0 ? Cr[(size_t)(i - 1) * W + j + c0 + 1] : 128;
+        q.lr = s_l ? Cr[(size_t)(i + r) * W + j - 1] : 128;
+        q.lb = s_l ? Cb[(size_t)(i + r) * W + j - 1] : 128;
+        return q;
+    };
+    Px nxt = fetch(0);
     for (int im = 0; im < mr; ++im) {
         const int i = im * 8;
         const bool s_u = im > 0;
         const size_t o = (size_t)(i + r) * W + j + c0;
-        const int yr0 = Cr[o], yr1 = Cr[o + 1], yb0 = Cb[o], yb1 = Cb[o + 1];
+        const Px cur = nxt;
+        if (im + 1 < mr) nxt = fetch(im + 1);
+        const int yr0 = cur.yr0, yr1 = cur.yr1, yb0 = cur.yb0, yb1 = cur.yb1;
         // up neighbours of this lane's two columns: Cr from the image, Cb from the RESIDUAL row above (:266)
-        const int ur0 = s_u ? Cr[(size_t)(i - 1) * W + j + c0] : 128, ur1 = s_u ? Cr[(size_t)(i - 1) * W + j + c0 + 1] : 128;
+        const int ur0 = cur.ur0, ur1 = cur.ur1;
         const int src = 28 + (lane & 3);   // lanes holding row 7 of the block above
         const int pb0 = __shfl_sync(0xffffffffu, prev_b0, src), pb1 = __shfl_sync(0xffffffffu, prev_b1, src);
         const int ub0 = s_u ? pb0 : 128, ub1 = s_u ? pb1 : 128;
-        const int lr = s_l ? Cr[(size_t)(i + r) * W + j - 1] : 128, lb = s_l ? Cb[(size_t)(i + r) * W + j - 1] : 128;
+        const int lr = cur.lr, lb = cur.lb;
         // dc = (sum(u) + sum(l)) // 16, floor division (Cb sums can be negative)
         int sr = (r == 0 ? ur0 + ur1 : 0) + ((lane & 3) == 0 ? lr : 0);
         int sb = (r == 0 ? ub0 + ub1 : 0) + ((lane & 3) == 0 ? lb : 0);
@@ -244,16 +261,17 @@ __global__ void intra_chroma8x8_kernel(const uint8_t *__restrict__ Cr, const uin
             sb += __shfl_xor_sync(0xffffffffu, sb, k);
         }
         const int dcr = fdiv_i(sr, 16), dcb = fdiv_i(sb, 16);
-        long long d0 = (long long)abs(ur0 - yr0) + abs(ur1 - yr1) + abs(ub0 - yb0) + abs(ub1 - yb1);
-        long long d1 = (long long)abs(lr - yr0) + abs(lr - yr1) + abs(lb - yb0) + abs(lb - yb1);
-        long long d2 = (long long)abs(dcr - yr0) + abs(dcr - yr1) + abs(dcb - yb0) + abs(dcb - yb1);
+        // |.| <= 510 per term (Cb's up neighbour is a residual in [-255, 255]), 128 terms per mode: int32 is ample
+        int d0 = abs(ur0 - yr0) + abs(ur1 - yr1) + abs(ub0 - yb0) + abs(ub1 - yb1);
+        int d1 = abs(lr - yr0) + abs(lr - yr1) + abs(lb - yb0) + abs(lb - yb1);
+        int d2 = abs(dcr - yr0) + abs(dcr - yr1) + abs(dcb - yb0) + abs(dcb - yb1);
 #pragma unroll
         for (int k = 16; k > 0; k >>= 1) {
-            d0 += (long long)shfl_xor_u64((unsigned long long)d0, k);
-            d1 += (long long)shfl_xor_u64((unsigned long long)d1, k);
-            d2 += (long long)shfl_xor_u64((unsigned long long)d2, k);
+            d0 += __shfl_xor_sync(0xffffffffu, d0, k);
+            d1 += __shfl_xor_sync(0xffffffffu, d1, k);
+            d2 += __shfl_xor_sync(0xffffffffu, d2, k);
         }
-        long long best = 2 * 8 * 8 * 255; int bmode = 0; bool any = false;
+        int best = 2 * 8 * 8 * 255, bmode = 0; bool any = false;
         if (d0 < best) { best = d0; bmode = 0; any = true; }
         if (d1 < best) { best = d1; bmode = 1; any = true; }
         if (d2 < best) { best = d2; bmode = 2; any = true; }

@@ -15,6 +15,8 @@
  *   - *_dev functions take DEVICE pointers, enqueue on the context's stream and do not
  *     synchronise; *_host functions take HOST pointers, copy in, run, copy out and return
  *     after the results are in the caller's buffers;
+ *   - device image buffers must be 4-byte aligned and device coefficient buffers 16-byte aligned (anything
+ *     from cudaMalloc or a torch tensor is); misaligned pointers are refused with VCS_E_INVALID;
  *   - there is no CPU fallback: without a CUDA device vcs_create fails.
  */
 #ifndef VCS_B200_H

@@ -90,3 +90,19 @@ def test_chroma_and_intra_stay_inside_their_buffers(shape):
         arena.check()
     finally:
         ctx.use_own_stream()
+
+
+def test_misaligned_device_buffers_are_refused():
+    import torch
+    import vcs_h264_b200 as v
+    from vcs_h264_b200 import _capi, runtime
+    H, W = 16, 32
+    ctx = runtime.get_context(0)
+    img = torch.zeros(H * W * 3 + 8, dtype=torch.uint8, device="cuda")
+    coef = torch.zeros(3 * H * W * 2 + 64, dtype=torch.uint8, device="cuda")
+    ctx.call("vcs_compress_dev", H, W, img.data_ptr(), _capi.COEF_I16_RINT, coef.data_ptr())          # aligned: fine
+    with pytest.raises(v.VcsError):
+        ctx.call("vcs_compress_dev", H, W, img.data_ptr() + 1, _capi.COEF_I16_RINT, coef.data_ptr())
+    with pytest.raises(v.VcsError):
+        ctx.call("vcs_compress_dev", H, W, img.data_ptr(), _capi.COEF_I16_RINT, coef.data_ptr() + 8)
+    torch.cuda.synchronize()

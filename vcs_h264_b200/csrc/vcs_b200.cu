@@ -177,6 +177,12 @@ int launch_dct(vcs_ctx *ctx, cudaStream_t st, DctArgs &a, int nP) {
             return fail(ctx, VCS_E_INVALID, "int8 indices are not lossless for this Q (min %g < 9): use VCS_COEF_I16_RINT", qmin);
     }
     if (nP <= 0) return VCS_OK;
+    // vector accesses: coefficient rows go out as 8 x int8 / int16 / 2 x float64 (16-byte stores for the wide
+    // formats), pixel groups are read as aligned 32-bit words
+    if ((uintptr_t)a.coef & 15) return fail(ctx, VCS_E_INVALID, "coefficient buffer must be 16-byte aligned");
+    if (((uintptr_t)a.img | (uintptr_t)a.pred_in | (uintptr_t)a.recon |
+         (a.has_fa ? ((uintptr_t)a.fa.cur_base | (uintptr_t)a.fa.ref_base) : 0)) & 3)
+        return fail(ctx, VCS_E_INVALID, "image buffers must be 4-byte aligned");
     const bool inv = a.inverse && a.recon;
     if (!a.forward && !inv) return fail(ctx, VCS_E_INVALID, "nothing to do: no forward pass and no reconstruction");
     if (a.forward && !inv && !a.coef) return fail(ctx, VCS_E_INVALID, "forward pass without an output");

@@ -7,8 +7,8 @@ cost (wrapped uint8 difference, motion.py:146) and static test (threshold 2000, 
 motion-compensated residual, 8x8 DCT, quantise QF=50 (rint -> int8 indices, lossless at this QF), dequantise, IDCT,
 reconstruction.  One "step" = one pass over one such clip per GPU; `value` = frames of all ranks
 / max-over-ranks device time with the clip resident in HBM; `e2e` = the same through
-vcs_encode_clip_host with pinned HOST buffers (H2D of the clip and D2H of MVs + indices inside
-the timed region).  The same numbers for the generalised true-SAD cost ride along in "sad_mode".
+vcs_encode_clip_host with pinned HOST buffers (H2D of the clip and D2H of MVs, costs, flags and indices inside
+the timed region; this leg does not ask for the reconstruction, so its DCT stage runs forward only).  The same numbers for the generalised true-SAD cost ride along in "sad_mode".
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 N > 1: launched by torch.distributed.run, one rank per GPU (weak scaling: one clip per rank, no

@@ -143,3 +143,14 @@ print("OK", r)
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("OK") == 2
+
+
+def test_only_tests_bench_and_smoke_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package or tools/ may import it."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle|.*libvcs_oracle)", re.M)
+    for f in glob.glob(os.path.join(root, "tools", "*.py")) + glob.glob(os.path.join(root, "vcs_h264_b200", "**", "*.py"), recursive=True):
+        assert not pat.search(open(f).read()), f

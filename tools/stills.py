@@ -48,9 +48,8 @@ def main():
                      "decompress_GBps": px * (6 + 3) / (times["decompress"] * 1e-3) / 1e9,
                      "sparsity": sp, "psnr_db": psnr})
     # intra mode decision on the same 4K still (IntraframeCompression/intraframe.py:24-317)
-    from oracle import oracle as orc   # colour split only (test-side helper, not timed)
-    ycc = orc.bgr2ycrcb(stills[0].cpu().numpy())
-    Y, Cr, Cb = (torch.from_numpy(np.ascontiguousarray(ycc[..., k])).cuda() for k in range(3))
+    # any uint8 planes will do for timing: the still's own B, G, R channels stand in for Y, Cr, Cb
+    Y, Cr, Cb = (stills[0][..., k].contiguous() for k in range(3))
     o = [torch.empty((H, W), dtype=torch.int32, device="cuda") for _ in range(4)]
     m4 = torch.empty((H // 4, W // 4), dtype=torch.uint8, device="cuda")
     intra = {}

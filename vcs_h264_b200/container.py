@@ -1,0 +1,104 @@
+"""Packed container of an encoded clip -- the wire form of the reference's list of `Frame` objects.
+
+The reference keeps an encoded clip as Python objects: `Frame(.t .mv .r .c .i .ref_i)` (frame.py:1-8) with the motion
+vectors as lists of Python ints, the residual as three float64 planes, and the I-frames kept aside in
+`Encoder.ref_frames` (encoder.py:38-43); it has no bitstream.  This module gives that state a byte layout, which is
+what crosses NCCL and what a file would hold:
+
+    header  (little endian, 64 bytes): magic "VCSB200\\0", version u32, T u32, H u32, W u32, block_size u32,
+            gop_len u32, coef_mode u32, n_p u32, n_blocks u32, qf f64, reserved
+    Q       float64[3][8][8]
+    I-frames uint8[n_i][H][W][3]                  (frame index t = k * gop_len)
+    mv      int16[n_p][n_blocks][2]  ([dx, dy], raster order: MotionProcessor.process_motion_prediction)
+    coef    [n_p][3][H][W] in the clip's coefficient format (float64 like DCTCompressor.compress, int16 or int8 indices)
+
+`to_frames()` rebuilds the reference's own objects (Frame lists, block coords, ref_frames) from a container, so the
+reference's Decoder -- or this package's drop-in Decoder -- can consume it unchanged.  No entropy stage: with the
+reference's wrapped residual the indices are dense (43 % non-zero at QF 50 on the bench clip).
+"""
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+from . import _capi
+from .frame import Frame
+
+MAGIC = b"VCSB200\0"
+VERSION = 1
+_HDR = struct.Struct("<8s9Id12x")
+COEF_DTYPES = {_capi.COEF_F64: np.float64, _capi.COEF_F64_RINT: np.float64,
+               _capi.COEF_I16_RINT: np.int16, _capi.COEF_I8_RINT: np.int8}
+
+
+def pack(i_frames, mv, coef, *, T, block_size, gop_len, coef_mode, qf=50.0, Q=None) -> bytes:
+    """i_frames uint8 [n_i,H,W,3]; mv int16 [n_p,N,2]; coef [n_p,3,H,W] (dtype of coef_mode)."""
+    i_frames = np.ascontiguousarray(i_frames, np.uint8)
+    n_i, H, W, _ = i_frames.shape
+    n_p = _capi.num_p_frames(T, gop_len)
+    N = (H // block_size) * (W // block_size)
+    mv = np.ascontiguousarray(mv, np.int16)
+    coef = np.ascontiguousarray(coef, COEF_DTYPES[coef_mode])
+    if n_i != (T + gop_len - 1) // gop_len or mv.shape != (n_p, N, 2) or coef.shape != (n_p, 3, H, W):
+        raise ValueError("array shapes do not match T / gop_len / block_size")
+    Q = np.ascontiguousarray(_capi.q_tables(qf) if Q is None else Q, np.float64).reshape(3, 8, 8)
+    hdr = _HDR.pack(MAGIC, VERSION, T, H, W, block_size, gop_len, coef_mode, n_p, N, float(qf))
+    return b"".join([hdr, Q.tobytes(), i_frames.tobytes(), mv.tobytes(), coef.tobytes()])
+
+
+def unpack(buf) -> dict:
+    """Inverse of pack(): dict(T, H, W, block_size, gop_len, coef_mode, qf, Q, i_frames, mv, coef) -- arrays are views."""
+    buf = memoryview(buf)
+    if len(buf) < _HDR.size:
+        raise ValueError("truncated container")
+    magic, ver, T, H, W, bs, gop, cm, n_p, N, qf = _HDR.unpack(buf[:_HDR.size])
+    if magic != MAGIC or ver != VERSION:
+        raise ValueError("not a vcs_b200 container (magic / version)")
+    if cm not in COEF_DTYPES or gop < 2 or bs < 1 or n_p != _capi.num_p_frames(T, gop) or N != (H // bs) * (W // bs):
+        raise ValueError("inconsistent container header")
+    n_i = (T + gop - 1) // gop
+    dt = np.dtype(COEF_DTYPES[cm])
+    sizes = [3 * 64 * 8, n_i * H * W * 3, n_p * N * 2 * 2, n_p * 3 * H * W * dt.itemsize]
+    if len(buf) != _HDR.size + sum(sizes):
+        raise ValueError("container size does not match its header")
+    off, parts = _HDR.size, []
+    for n in sizes:
+        parts.append(buf[off:off + n])
+        off += n
+    return dict(T=T, H=H, W=W, block_size=bs, gop_len=gop, coef_mode=cm, qf=qf,
+                Q=np.frombuffer(parts[0], np.float64).reshape(3, 8, 8),
+                i_frames=np.frombuffer(parts[1], np.uint8).reshape(n_i, H, W, 3),
+                mv=np.frombuffer(parts[2], np.int16).reshape(n_p, N, 2),
+                coef=np.frombuffer(parts[3], dt).reshape(n_p, 3, H, W))
+
+
+def to_frames(c: dict):
+    """(encoded_frames, ref_frames) exactly as Encoder leaves them (encoder.py:38-70): I-frames are
+    Frame("I", None, None, None, t, ref_idx) with the image in ref_frames; P-frames carry mv as [dx,dy] int lists,
+    r as three float64 planes (the rounded indices as floats when the clip holds indices) and c as [x,y] coords."""
+    H, W, bs, g = c["H"], c["W"], c["block_size"], c["gop_len"]
+    coords = [[x, y] for y in range(0, H - bs + 1, bs) for x in range(0, W - bs + 1, bs)]
+    frames, refs, p = [], [], 0
+    for t in range(c["T"]):
+        if t % g == 0:
+            refs.append(np.array(c["i_frames"][t // g]))
+            frames.append(Frame("I", None, None, None, t, t % g))          # encoder.py:43: frame_num % len(pattern)
+        else:
+            planes = [np.array(c["coef"][p, k], np.float64) for k in range(3)]
+            frames.append(Frame("P", np.asarray(c["mv"][p], np.int64).tolist(), planes, coords, t, t // g))
+            p += 1
+    return frames, refs
+
+
+def from_frames(encoded_frames, ref_frames, *, block_size, gop_len, coef_mode=_capi.COEF_F64, qf=50.0, Q=None) -> bytes:
+    """pack() from the reference-style objects: Encoder.encoded_frames and Encoder.ref_frames."""
+    T = len(encoded_frames)
+    P = [f for f in encoded_frames if f.t == "P"]
+    i_frames = np.stack([np.asarray(r, np.uint8) for r in ref_frames])
+    H, W = i_frames.shape[1:3]
+    N = (H // block_size) * (W // block_size)
+    mv = np.asarray([f.mv for f in P], np.int16).reshape(len(P), N, 2)
+    coef = np.stack([np.stack([np.asarray(pl) for pl in f.r]) for f in P]) if P else np.zeros((0, 3, H, W))
+    return pack(i_frames, mv, coef.astype(COEF_DTYPES[coef_mode]), T=T, block_size=block_size, gop_len=gop_len,
+                coef_mode=coef_mode, qf=qf, Q=Q)

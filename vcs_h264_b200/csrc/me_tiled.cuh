@@ -29,10 +29,12 @@
 
 #include "common.cuh"
 
-// wrap8 loop: VCS_WRAP_ALU_NUM of every VCS_WRAP_ALU_DEN subtracts are forced onto the ALU pipe (IADD3), the rest
-// go to the FMA pipe (IMAD.IADD); 2 of 5 measured best (tools/ab_me.sh builds and times other splits).
-#ifndef VCS_WRAP_ALU_NUM
-#define VCS_WRAP_ALU_NUM 2
+// wrap8 loop: the subtracts of the offsets d with bit (d mod VCS_WRAP_ALU_DEN) set in VCS_WRAP_ALU_MASK are forced onto
+// the ALU pipe (IADD3), the rest go to the FMA pipe (IMAD.IADD); 2 of 5 measured best, and among the ten 2-of-5 masks
+// 0x6 (9.14 ms per 45 P-frames; the others 9.18-9.24: same instruction mix, different ptxas schedule) (tools/ab_me.sh builds and
+// times other splits).
+#ifndef VCS_WRAP_ALU_MASK
+#define VCS_WRAP_ALU_MASK 0x6
 #define VCS_WRAP_ALU_DEN 5
 #endif
 
@@ -345,7 +347,7 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
                                         // FMA); ptxas sends them all to FMA, where IDP.4A also lives.  A third
                                         // (opaque zero) addend forces IADD3 for 2 of 5 so both pipes fill up.
                                         uint32_t z;
-                                        if (d % VCS_WRAP_ALU_DEN < VCS_WRAP_ALU_NUM)
+                                        if ((VCS_WRAP_ALU_MASK >> (d % VCS_WRAP_ALU_DEN)) & 1)
                                             asm("{\n.reg .u32 t;\nsub.u32 t, %1, %2;\nadd.u32 t, t, %5;\n"
                                                 "lop3.b32 %0, t, %3, %4, 0x96;\n}"
                                                 : "=r"(z) : "r"(r1), "r"(c[v]), "r"(r2), "r"(chh[v]), "r"(zero));

@@ -139,6 +139,13 @@ int vcs_sub_wrap_host(vcs_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n
 int vcs_add_wrap_host(vcs_ctx *ctx, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
 
 /* ---- 8x8 DCT / quantise / dequantise / IDCT ---------------------------------------------- */
+/*
+ * DCTCompressor._dct2 / _idct2 (DCTcompressor.py:111-121) on n bare 8x8 float64 blocks, row-major, host
+ * buffers: out = C.X.C^T (inverse = 0) or C^T.X.C (inverse != 0), every element a sequential-k FMA chain
+ * like np.matmul.  Backs the private helpers of the drop-in class; the hot path is vcs_compress_* below.
+ */
+int vcs_dct2_blocks_host(vcs_ctx *ctx, int nblocks, int inverse, const double *in, double *out);
+
 /* DCTCompressor.compress (DCTcompressor.py:49-74; rounded: dct.py:169-186).  H, W must be
  * multiples of 8 (the reference would bilinear-resize; VCS_E_INVALID here).  coef: 3 planes
  * H x W of float64 (VCS_COEF_F64*), int16 (VCS_COEF_I16_RINT) or int8 (VCS_COEF_I8_RINT), order Y, Cr, Cb. */

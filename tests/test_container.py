@@ -9,7 +9,11 @@ from vcs_h264_b200 import _capi, container
 def _random_clip(rng, T=7, H=32, W=48, bs=8, gop=3, cm=_capi.COEF_I16_RINT):
     n_i, n_p, N = (T + gop - 1) // gop, _capi.num_p_frames(T, gop), (H // bs) * (W // bs)
     i_frames = rng.integers(0, 256, (n_i, H, W, 3), dtype=np.uint8)
-    mv = rng.integers(-16, 17, (n_p, N, 2)).astype(np.int16)
+    # in-frame vectors only: unpack() refuses a vector that would move its macroblock out of the frame
+    k = np.arange(N)
+    x, y = (k % (W // bs)) * bs, (k // (W // bs)) * bs
+    tx, ty = rng.integers(0, W - bs + 1, (n_p, N)), rng.integers(0, H - bs + 1, (n_p, N))
+    mv = np.stack([tx - x, ty - y], -1).astype(np.int16)
     dt = container.COEF_DTYPES[cm]
     coef = rng.integers(-100, 101, (n_p, 3, H, W)).astype(dt) if dt != np.float64 else rng.standard_normal((n_p, 3, H, W))
     return dict(i_frames=i_frames, mv=mv, coef=coef, T=T, block_size=bs, gop_len=gop, coef_mode=cm)
@@ -40,6 +44,11 @@ def test_rejects_damaged_containers():
         container.unpack(blob[:40])
     with pytest.raises(ValueError):
         container.pack(c["i_frames"][:1], c["mv"], c["coef"], T=c["T"], block_size=8, gop_len=3, coef_mode=c["coef_mode"])
+    bad = c["mv"].copy()
+    bad[1, 3, 0] = 1000                      # a vector that leaves the frame (corrupt or foreign input)
+    with pytest.raises(ValueError, match="outside the frame"):
+        container.unpack(container.pack(c["i_frames"], bad, c["coef"], T=c["T"], block_size=8, gop_len=3,
+                                        coef_mode=c["coef_mode"]))
 
 
 def test_frames_view_matches_the_reference_objects():

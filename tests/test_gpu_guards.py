@@ -106,3 +106,84 @@ def test_misaligned_device_buffers_are_refused():
     with pytest.raises(v.VcsError):
         ctx.call("vcs_compress_dev", H, W, img.data_ptr(), _capi.COEF_I16_RINT, coef.data_ptr() + 8)
     torch.cuda.synchronize()
+
+
+def test_private_dct_helpers_match_the_oracle(orc):
+    """DCTCompressor._dct2 / _idct2 (DCTcompressor.py:111-121) on the CUDA path, bit for bit."""
+    import vcs_h264_b200 as v
+    dc = v.DCTCompressor(8)
+    rng = np.random.default_rng(5)
+    for _ in range(8):
+        x = rng.integers(-128, 128, (8, 8)).astype(np.float64)
+        d = dc._dct2(x)
+        assert np.array_equal(d, orc.dct2(x))
+        assert np.array_equal(dc._idct2(d), orc.idct2(d))
+    assert np.array_equal(dc._dctMatrix(), orc.dct_matrix())
+
+
+def test_out_of_frame_vectors_are_refused_not_followed():
+    """*_dev paths never follow a motion vector out of the frame (corrupt or foreign input): the prediction is zero
+    there and the context reports it at the next synchronisation."""
+    import torch
+    import vcs_h264_b200 as v
+    from vcs_h264_b200 import synth
+    T, H, W, bs, gop = 4, 64, 96, 16, 4
+    clip = torch.from_numpy(synth.clip(T, H, W, seed=9, margin=48)).cuda()
+    ce = v.ClipEncoder([H, W], block_size=bs, search="full", search_range=8, gop_len=gop, coef_mode=v.COEF_I16_RINT)
+    out = ce.alloc_device_outputs(T)
+    ce.encode_device(clip, out)
+    torch.cuda.synchronize()
+    cd = v.ClipDecoder([H, W], block_size=bs, gop_len=gop, coef_mode=v.COEF_I16_RINT)
+    rec = torch.empty_like(out["recon"])
+    cd.decode_device(clip[::gop].contiguous(), out["mv"], out["coef"], rec, T)
+    cd.ctx.synchronize()
+    assert torch.equal(rec, out["recon"])
+    bad = out["mv"].clone()
+    bad[1, 7, 0] = 30000                                   # far outside the frame
+    bad[2, 0, 1] = -5                                      # above the top edge
+    cd.decode_device(clip[::gop].contiguous(), bad, out["coef"], rec, T)
+    with pytest.raises(v.VcsError, match="outside the frame"):
+        cd.ctx.synchronize()
+    cd.ctx.synchronize()                                   # reported once, then clear
+    # the good macroblocks are unaffected
+    assert torch.equal(rec[0], out["recon"][0])
+
+
+def test_front_ends_do_not_share_quantiser_state():
+    """Two encoders with different QF on one device keep their own tables (each owns a context)."""
+    import torch
+    import vcs_h264_b200 as v
+    from vcs_h264_b200 import synth
+    T, H, W = 2, 64, 96
+    clip = torch.from_numpy(synth.clip(T, H, W, seed=3, margin=48)).cuda()
+    a = v.ClipEncoder([H, W], block_size=16, search_range=8, gop_len=2, qf=50.0, coef_mode=v.COEF_I16_RINT)
+    oa = a.alloc_device_outputs(T)
+    a.encode_device(clip, oa)
+    torch.cuda.synchronize()
+    want = oa["coef"].clone()
+    b = v.ClipEncoder([H, W], block_size=16, search_range=8, gop_len=2, qf=90.0, coef_mode=v.COEF_I16_RINT)
+    ob = b.alloc_device_outputs(T)
+    b.encode_device(clip, ob)
+    v.DCTCompressor(8).compress(np.zeros((8, 8, 3), np.uint8))      # the shared drop-in context, QF 50 tables
+    a.encode_device(clip, oa)
+    torch.cuda.synchronize()
+    assert torch.equal(oa["coef"], want) and not torch.equal(ob["coef"], want)
+
+
+def test_two_devices_in_one_process():
+    """Contexts on two devices interleave their calls; each entry point selects its own device and puts the
+    caller's back."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import vcs_h264_b200 as v
+    from vcs_h264_b200 import synth
+    T, H, W = 3, 64, 96
+    clip = synth.clip(T, H, W, seed=4, margin=48)
+    enc = [v.ClipEncoder([H, W], block_size=16, search_range=8, gop_len=3, coef_mode=v.COEF_I16_RINT, device=d) for d in (0, 1)]
+    torch.cuda.set_device(0)
+    outs = [e.encode_host(clip, want_coef=True, want_recon=True) for e in (enc[1], enc[0], enc[1])]
+    assert torch.cuda.current_device() == 0
+    for o in outs[1:]:
+        for k in ("mv", "coef", "recon"):
+            assert np.array_equal(np.asarray(o[k]), np.asarray(outs[0][k])), k

@@ -92,6 +92,28 @@ def test_dropin_surface():
     assert enc.ENCODING_PATTERN_LENGTH == 4 and enc.ref_frames == [] and enc.encoded_frames == []
     with pytest.raises(ValueError):
         v.DCTCompressor(16).compress(np.zeros((16, 16, 3), np.uint8))
+    # private helpers and attributes the reference's classes carry (DCTcompressor.py:100-139, decoder.py:16)
+    for name in ("_dct2", "_idct2", "_dctMatrix", "_cuHelper", "_completeDCT", "compress", "decompress"):
+        assert callable(getattr(dc, name)), name
+    assert dc._cuHelper(0) == 2 ** -0.5 and dc._cuHelper(3) == 1
+    from vcs_h264_b200 import DCTcompressor as dmod
+    assert (dmod.QF, dmod.TEST_COMPRESSOR, dmod.QUANTIZE) == (50.0, False, False) and len(dmod.Q) == 3
+    dec = v.Decoder([], 25, [360, 640], [], 8, True)
+    assert dec.fourcc == 875967064                       # cv2.VideoWriter_fourcc(*'X264')
+    for name in ("reconstruct_video", "_fully_reconstruct", "_reconstruct_P_frame"):
+        assert callable(getattr(dec, name)), name
+    for name in ("encode_frame", "_process_I_frame", "_process_B_frame", "_process_P_frame"):
+        assert callable(getattr(enc, name)), name
+
+
+def test_import_has_no_side_effects():
+    """Importing the package (or its synth module) neither dlopens the CUDA library nor compiles anything;
+    bench.py's reference arm relies on that."""
+    code = ("import sys; sys.path.insert(0, %r); import vcs_h264_b200, vcs_h264_b200.synth, vcs_h264_b200.DCTcompressor;"
+            "maps = open('/proc/self/maps').read(); assert 'libvcs_b200' not in maps, 'library mapped at import';"
+            "from vcs_h264_b200 import _capi; assert _capi._lib is None; print('clean')") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stdout + r.stderr
 
 
 def test_sharding_ranges():

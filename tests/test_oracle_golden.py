@@ -149,3 +149,39 @@ def test_symmetric_search_properties(orc):
     for k in np.nonzero(same)[0]:
         if cost_s[k] == cost_l[k]:
             assert tuple(mv_s[k]) == tuple(mv_l[k])
+
+
+def test_traffic_cut_pins(orc):
+    """BASELINE configs[0] on the real clip: the oracle against sha256 pins taken from the UNMODIFIED reference
+    (tests/golden/make_golden_traffic.py) -- all 114 x 3600 motion vectors, static counts, and the float64 planes and
+    decoded frames of P-frames 1 and 35.  The clip is a data fixture copied from the reference's videos/."""
+    import hashlib
+    import json
+    import os
+    cv2 = pytest.importorskip("cv2")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(here, "golden_traffic_meta.json")) as f:
+        meta = json.load(f)
+    cap = cv2.VideoCapture(os.path.join(here, meta["file"]))
+    frames = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        frames.append(f)
+    cap.release()
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+    if len(frames) != meta["frames"] or sha(np.stack(frames)) != meta["frames_sha16"]:
+        pytest.skip("this host's video decoder yields different pixels than the one the pins were taken with")
+    prm = orc.reference_search_params(8)
+    mvs = [orc.me(f, frames[(n // 4) * 4], 8, **prm)[0] for n, f in enumerate(frames) if n % 4]
+    mv = np.stack(mvs).astype(np.int32)
+    assert sha(mv) == meta["mv_sha16"]
+    statics = [int(((m[:, 0] == 0) & (m[:, 1] == 0)).sum()) for m in mv]
+    assert [min(statics), max(statics)] == meta["static_minmaxmean"][:2]
+    for n in (1, 35):
+        o = orc.encode_p(frames[n], frames[(n // 4) * 4], 8, **prm)
+        assert sha(o["planes"]) == meta[f"frame{n}_planes_sha16"]
+        assert sha(o["recon"]) == meta[f"frame{n}_final_sha16"]

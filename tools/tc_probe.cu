@@ -1,0 +1,422 @@
+// tc_probe.cu -- can the 5th-gen tensor core be the BYTE-SUM engine of the wrapped-cost search? (sm_100a)
+//
+// The wrapped cost of the reference (motion.py:146) needs, per 4 bytes, a borrow-isolated subtract, a 3-input
+// xor and a sum of the 4 result bytes.  The byte sum is IDP.4A today (1 of 3 issue slots).  This probe moves
+// it to tcgen05.mma.kind::i8: every thread writes its result words z to TMEM (tcgen05.st.32x32b, A operand,
+// row = thread, 4 K-bytes per 32-bit column), B is a 0/1 selector matrix in shared memory that routes word j
+// of a row to accumulator column j, D accumulates in TMEM.
+//
+//   part 1 (mode 0..7)  : correctness of one MMA against a host byte sum, for the B layouts / D column
+//                         offsets the kernel would need (which LBO/SBO reading is right, is an unaligned
+//                         D base legal, N = 8).
+//   part 2 (mode 10..15): throughput of the producer/consumer pipeline (16 worker warps compute z, one
+//                         thread issues MMAs) against the IDP.4A loop it would replace.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/tc_probe tools/tc_probe.cu
+//   for m in 0 1 2 3 4 5 6 7 10 11 12 13 14 15; do timeout 60 tools/tc_probe $m; done
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); return 2; } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: returns false on timeout (the probe must never hang the box)
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int max_tries = 1 << 20) {
+    for (int t = 0; t < max_tries; ++t) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t *v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]; int8 kinds; one thread issues
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_alloc(uint32_t *slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor): address, LBO, SBO in 16-byte units
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;   // version = 1 (Blackwell)
+    return d;                 // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): S32 accumulate, unsigned 8-bit A and B, A K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn_major) {
+    return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__host__ __device__ inline uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// part 1: one CTA of 128 threads, two MMAs (K = 32 each) into one N-wide accumulator block
+//   mode 0: B N-major (byte k*16+n), N=16        mode 1: B K-major, LBO=128 (k half), SBO=256 (n group)
+//   mode 2: B K-major with LBO/SBO swapped       mode 3/4/5: mode 0 with the D base at column +8 / +4 / +1
+//   mode 6: N=8 (K-major, one n group)           mode 7: mode 0, N=32 (selector into columns 16..31)
+__global__ void __launch_bounds__(128, 1) k_check(int mode, uint32_t *out, uint32_t *status) {
+    __shared__ __align__(128) uint8_t sB[2][1024];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int N = mode == 6 ? 8 : (mode == 7 ? 32 : 16);
+    const int dofs = mode == 3 ? 8 : (mode == 4 ? 4 : (mode == 5 ? 1 : 0));
+    // selector: MMA q routes word j (K bytes 4j..4j+3) to column 8q + j (+16 in mode 7)
+    for (int i = tid; i < 2 * 1024; i += 128) (&sB[0][0])[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < 2 * 32; i += 128) {
+        const int q = i / 32, k = i % 32;
+        int n = (mode == 6 ? 0 : 8 * q) + k / 4 + (mode == 7 ? 16 : 0);
+        if (mode == 6 && q == 1) n = 7 - k / 4;        // second MMA: reversed routing
+        uint32_t off;
+        if (mode == 1 || mode == 6) off = (n % 8) * 16 + (n / 8) * 256 + (k % 16) + (k / 16) * 128;
+        else if (mode == 2) off = (n % 8) * 16 + (n / 8) * 128 + (k % 16) + (k / 16) * 256;
+        else off = k * N + n;                          // N-major: N contiguous bytes per k (N=16: 16 B rows; N=32: see below)
+        if (mode == 7) off = (n / 16) * 512 + k * 16 + (n % 16);   // two 16-wide n groups, SBO = 512
+        sB[q][off] = 1;
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tc_alloc(&tmem_slot, 64);
+    // make the generic-proxy writes of B visible to the async proxy (the MMA reads smem through it)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    const uint32_t lane_base = tbase + ((uint32_t)(32 * warp) << 16);
+    // columns: D at [0, 40) (N <= 32 plus offset), A at [48, 64)
+    uint32_t zeros[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) zeros[j] = 0;
+    tc_st16(lane_base + 0, zeros);
+    tc_st16(lane_base + 16, zeros);
+    tc_st8(lane_base + 32, zeros);
+    uint32_t a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = hash32(tid * 16 + j + 1);
+    tc_st16(lane_base + 48, a);
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc(128, N, (mode == 1 || mode == 2 || mode == 6) ? 0 : 1);
+        for (int q = 0; q < 2; ++q) {
+            uint64_t desc;
+            const uint32_t sa = smem_u32(&sB[q][0]);
+            if (mode == 1 || mode == 6) desc = make_desc(sa, 128, 256);
+            else if (mode == 2) desc = make_desc(sa, 256, 128);
+            else if (mode == 7) desc = make_desc(sa, 128, 512);
+            else desc = make_desc(sa, 128, 128);
+            tc_mma_i8_ts(tbase + dofs, tbase + 48 + 8 * q, desc, idesc, 1);
+        }
+        tc_commit(&bar);
+    }
+    const bool ok = mbar_wait(&bar, 0);
+    tc_fence_after();
+    uint32_t d[16], d2[16], d3[16];
+    tc_ld16(lane_base + 0, d);
+    tc_ld16(lane_base + 16, d2);
+    tc_ld16(lane_base + 24, d3);
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { out[tid * 40 + j] = d[j]; out[tid * 40 + 16 + j] = d2[j]; }
+#pragma unroll
+    for (int j = 8; j < 16; ++j) out[tid * 40 + 24 + j] = d3[j];
+    if (!ok) atomicAdd(status, 1);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc_dealloc(tbase, 64);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// part 2: throughput.  16 worker warps, each iteration ("row step") = one window-row word used against the 16
+// macroblock rows: 16 x (subtract, 3-input xor) [+ 16 x IDP.4A in the baseline], like the search kernel's loop.
+//   mode 10: baseline, IDP.4A byte sums in registers (today's loop)
+//   mode 11: subtract + xor only (no byte sum at all): the ALU floor of the tensor variant
+//   mode 12: + tcgen05.st.x16 of the 16 results + wait::st every step (no MMA, no barriers)
+//   mode 13: full pipeline: st -> (4 warps of a lane-quarter group arrive) -> MMA thread issues 2 MMAs -> commit
+//            frees the buffer; NBUF A buffers per group
+//   mode 14: as 13 but wait::st / arrive deferred by one step (the st of step i overlaps the ALU work of i+1)
+//   mode 15: as 14 with steps of 2 rows (32 results, 2 st.x16, 4 MMAs per arrive)
+constexpr int WORKERS = 16;
+struct Pipe {
+    uint64_t full[4][4], empty[4][4];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(32 * (WORKERS + 1), 1) k_pipe(int iters, uint32_t seed, uint32_t *out, long long *cyc, uint32_t *status) {
+    __shared__ __align__(128) uint8_t sB[2][512];
+    __shared__ Pipe pipe;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int ROWS = MODE == 15 ? 2 : 1;            // window rows per step
+    constexpr int NBUF = ROWS == 2 ? 3 : 4;             // A buffers per group: 16 + 16*ROWS*NBUF <= 128 columns
+    for (int i = tid; i < 2 * 512; i += blockDim.x) (&sB[0][0])[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < 2 * 32; i += blockDim.x) { const int q = i / 32, k = i % 32; sB[q][k * 16 + 8 * q + k / 4] = 1; }
+    if (tid == 0) {
+        for (int g = 0; g < 4; ++g)
+            for (int b = 0; b < NBUF; ++b) { mbar_init(&pipe.full[g][b], 4); mbar_init(&pipe.empty[g][b], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tc_alloc(&tmem_slot, 512);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    // group g = warp / 4 owns columns [128 g, 128 g + 128): D at +0 (16 columns), A buffers at +16 + 16*ROWS*b
+    const int g = (warp / 4) & 3, quarter = warp & 3;
+    const uint32_t gcol = 128u * g;
+    const uint32_t lane_base = tbase + ((uint32_t)(32 * quarter) << 16) + gcol;
+    long long t0 = 0;
+    bool ok = true;
+    if (warp < WORKERS) {
+        uint32_t c[16], ch[16], acc[16], z[16 * ROWS];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { c[j] = hash32(seed + tid * 16 + j) & 0x7f7f7f7fu; ch[j] = hash32(seed * 3 + tid * 16 + j) & 0x80808080u; acc[j] = 0; }
+        uint32_t r = hash32(seed + tid);
+        {
+            uint32_t zeros[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) zeros[j] = 0;
+            tc_st16(lane_base, zeros);
+            tc_wait_st();
+        }
+        __syncwarp();
+        t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            const int b = it % NBUF;
+            const uint32_t par = (uint32_t)(it / NBUF) & 1;
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr) {
+                r = r * 1664525u + 1013904223u;                      // the next window word (stands in for the LDS)
+                uint32_t r1, r2;
+                asm volatile("lop3.b32 %0, %1, %2, %2, 0xfc;" : "=r"(r1) : "r"(r), "r"(0x80808080u));
+                r2 = r1 - r;                                         // ~r & H on the FMA pipe
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    uint32_t zz;
+                    asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(zz) : "r"(r1 - c[j]), "r"(r2), "r"(ch[j]));
+                    if (MODE == 10) acc[j] = __dp4a(zz, 0x01010101u, acc[j]);
+                    else if (MODE == 11) ch[j] = zz;                 // the result feeds the next step's xor: 2 instructions per word, all live
+                    else z[16 * rr + j] = zz;
+                }
+            }
+            if (MODE == 12) {
+#pragma unroll
+                for (int rr = 0; rr < ROWS; ++rr) tc_st16(lane_base + 16 + 16 * rr, z + 16 * rr);
+                tc_wait_st();
+            }
+            if (MODE >= 13) {
+                if (MODE >= 14 && it > 0) {                          // finish the previous step's stores
+                    tc_wait_st();
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(&pipe.full[g][(it - 1) % NBUF]);
+                }
+                if (it >= NBUF) ok = ok && mbar_wait(&pipe.empty[g][b], par ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int rr = 0; rr < ROWS; ++rr) tc_st16(lane_base + 16 + 16 * ROWS * b + 16 * rr, z + 16 * rr);
+                if (MODE == 13) {
+                    tc_wait_st();
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(&pipe.full[g][b]);
+                }
+            }
+        }
+        if (MODE >= 14) {
+            tc_wait_st();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&pipe.full[g][(iters - 1) % NBUF]);
+        }
+        uint32_t s = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s += acc[j] + (MODE == 11 ? ch[j] : 0u);
+        out[blockIdx.x * blockDim.x + tid] = s + r;
+    } else if (MODE >= 13) {
+        // the MMA warp: one thread walks (step, group) in order
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, 16, 1);
+            const uint64_t d0 = make_desc(smem_u32(&sB[0][0]), 128, 128), d1 = make_desc(smem_u32(&sB[1][0]), 128, 128);
+            for (int it = 0; it < iters && ok; ++it) {
+                const int b = it % NBUF;
+                const uint32_t par = (uint32_t)(it / NBUF) & 1;
+                for (int gg = 0; gg < 4; ++gg) {
+                    ok = ok && mbar_wait(&pipe.full[gg][b], par);
+                    tc_fence_after();
+                    const uint32_t col = tbase + 128u * gg;
+#pragma unroll
+                    for (int rr = 0; rr < ROWS; ++rr) {
+                        tc_mma_i8_ts(col, col + 16 + 16 * ROWS * b + 16 * rr, d0, idesc, 1);
+                        tc_mma_i8_ts(col, col + 16 + 16 * ROWS * b + 16 * rr + 8, d1, idesc, 1);
+                    }
+                    tc_commit(&pipe.empty[gg][b]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (tid == 0) cyc[blockIdx.x] = t1 - t0;
+    if (!ok) atomicAdd(status, 1);
+    // drain: every MMA must have completed before TMEM goes away
+    tc_fence_before();
+    __syncthreads();
+    if (MODE >= 13 && warp == WORKERS && lane == 0) {
+        // last commits: wait until the final buffer of every group is free again
+        for (int gg = 0; gg < 4; ++gg) {
+            const int it = iters - 1;
+            mbar_wait(&pipe.empty[gg][it % NBUF], (uint32_t)(it / NBUF) & 1);
+        }
+    }
+    __syncthreads();
+    tc_fence_after();
+    if (MODE >= 13 && warp < WORKERS && (warp & 3) == quarter) {
+        uint32_t d[16];
+        tc_ld16(lane_base, d);
+        tc_wait_ld();
+        uint32_t s = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s += d[j];
+        out[blockIdx.x * blockDim.x + tid] += s;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc_dealloc(tbase, 512);
+}
+
+static int run_check(int mode) {
+    uint32_t *d_out, *d_status;
+    CK(cudaMalloc(&d_out, 128 * 40 * 4));
+    CK(cudaMalloc(&d_status, 4));
+    CK(cudaMemset(d_out, 0xff, 128 * 40 * 4));
+    CK(cudaMemset(d_status, 0, 4));
+    k_check<<<1, 128>>>(mode, d_out, d_status);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    static uint32_t h[128 * 40];
+    uint32_t st;
+    CK(cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&st, d_status, 4, cudaMemcpyDeviceToHost));
+    const int dofs = mode == 3 ? 8 : (mode == 4 ? 4 : (mode == 5 ? 1 : 0));
+    int bad = 0, shown = 0;
+    for (int t = 0; t < 128; ++t) {
+        uint32_t want[40] = {0};
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t a = hash32(t * 16 + j + 1);
+            const uint32_t bs = (a & 255) + ((a >> 8) & 255) + ((a >> 16) & 255) + (a >> 24);
+            int col = j;
+            if (mode == 6) col = j < 8 ? j : 7 - (j - 8);
+            if (mode == 7) col = 16 + j;
+            want[dofs + col] += bs;
+        }
+        for (int j = 0; j < 40; ++j)
+            if (h[t * 40 + j] != want[j]) {
+                ++bad;
+                if (shown < 6) { printf("  row %d col %d: got %u want %u\n", t, j, h[t * 40 + j], want[j]); ++shown; }
+            }
+    }
+    printf("check mode %d: %s (%d mismatching cells, barrier timeouts %u)\n", mode, bad == 0 && st == 0 ? "PASS" : "FAIL", bad, st);
+    return bad != 0;
+}
+
+template <int MODE>
+static int run_pipe(int iters) {
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int threads = 32 * (WORKERS + 1);
+    uint32_t *d_out, *d_status; long long *d_cyc;
+    CK(cudaMalloc(&d_out, (size_t)sms * threads * 4));
+    CK(cudaMalloc(&d_cyc, sms * 8));
+    CK(cudaMalloc(&d_status, 4));
+    CK(cudaMemset(d_status, 0, 4));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    k_pipe<MODE><<<sms, threads>>>(iters / 8 + 1, 1234u, d_out, d_cyc, d_status);
+    CK(cudaEventRecord(e0));
+    k_pipe<MODE><<<sms, threads>>>(iters, 1234u, d_out, d_cyc, d_status);
+    CK(cudaEventRecord(e1));
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    long long cyc; uint32_t st;
+    CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&st, d_status, 4, cudaMemcpyDeviceToHost));
+    const int rows = MODE == 15 ? 2 : 1;
+    const double words = (double)iters * rows * 16;           // per thread
+    // per SMSP: 4 worker warps; clocks per word per warp-slot = cyc / (4 warps * words)
+    printf("pipe mode %d: %.3f ms, %lld clk for %d steps -> %.2f clk per row step per warp-quad slot, %.3f clk/word/SMSP, timeouts %u\n",
+           MODE, ms, cyc, iters, (double)cyc / (iters * rows) / 4.0, (double)cyc / (4.0 * words), st);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    const int mode = argc > 1 ? atoi(argv[1]) : 0;
+    const int iters = argc > 2 ? atoi(argv[2]) : 20000;
+    if (mode < 10) return run_check(mode);
+    switch (mode) {
+        case 10: return run_pipe<10>(iters);
+        case 11: return run_pipe<11>(iters);
+        case 12: return run_pipe<12>(iters);
+        case 13: return run_pipe<13>(iters);
+        case 14: return run_pipe<14>(iters);
+        case 15: return run_pipe<15>(iters);
+    }
+    return 1;
+}

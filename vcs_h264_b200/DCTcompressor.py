@@ -11,7 +11,22 @@ from . import _capi
 from .runtime import get_context
 
 QF = 50.0                      # DCTcompressor.py:29
-Q = list(_capi.q_tables(QF))   # [QY', QC', QC'] for (Y, Cr, Cb)  (DCTcompressor.py:36-38)
+TEST_COMPRESSOR = False        # DCTcompressor.py:7
+QUANTIZE = False               # DCTcompressor.py:8 (dead in the reference too)
+
+
+def _default_Q():
+    if "Q" not in globals():
+        globals()["Q"] = list(_capi.q_tables(QF))
+    return globals()["Q"]
+
+
+def __getattr__(name):
+    """Module attribute `Q` = [QY', QC', QC'] for (Y, Cr, Cb) (DCTcompressor.py:36-38), built on first use so
+    that importing the package neither loads nor needs the CUDA library."""
+    if name == "Q":
+        return _default_Q()
+    raise AttributeError(name)
 
 
 def quality_tables(qf):
@@ -23,7 +38,7 @@ class DCTCompressor:
     def __init__(self, block_size, device=0):
         self.blocksize = block_size
         self.compressed = []
-        self.Q = Q
+        self.Q = _default_Q()
         self._device = device
 
     def _ctx(self):
@@ -87,7 +102,31 @@ class DCTCompressor:
         print("decompression finished")
         return out
 
-    # -- private helpers the reference exposes (DCTcompressor.py:111-139) -----------------------
+    # -- private helpers the reference exposes (DCTcompressor.py:100-139) -----------------------
+    def _completeDCT(self, input_img):
+        """DCTcompressor.py:100-109: compress then decompress (the reference then plots the result with
+        matplotlib, which is the caller's business here); returns the round-tripped BGR image."""
+        imshape = input_img.shape
+        print("begin compression")
+        compressed = self.compress(input_img)
+        return self.decompress(compressed, imshape)
+
+    def _blocks(self, matrix, inverse):
+        m = np.ascontiguousarray(np.asarray(matrix, np.float64))
+        if m.shape != (8, 8) or self.blocksize != 8:
+            raise ValueError("only the 8x8 transform is built")
+        out = np.empty((8, 8), np.float64)
+        get_context(self._device).call("vcs_dct2_blocks_host", 1, int(inverse), m.ctypes.data, out.ctypes.data)
+        return out
+
+    def _dct2(self, matrix):
+        """DCTcompressor.py:111-115: C . matrix . C^T (two float64 products, sequential-k FMA like np.matmul)."""
+        return self._blocks(matrix, False)
+
+    def _idct2(self, matrix):
+        """DCTcompressor.py:117-121: C^T . matrix . C."""
+        return self._blocks(matrix, True)
+
     def _dctMatrix(self):
         if self.blocksize != 8:
             raise ValueError("only the 8x8 transform is built")

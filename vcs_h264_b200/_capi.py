@@ -69,6 +69,7 @@ SIGNATURES = {
     "vcs_add_wrap_dev": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "vcs_sub_wrap_host": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "vcs_add_wrap_host": (_i, [_vp, _vp, _vp, _sz, _vp]),
+    "vcs_dct2_blocks_host": (_i, [_vp, _i, _i, _vp, _vp]),
     "vcs_compress_dev": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "vcs_compress_host": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "vcs_decompress_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
@@ -96,16 +97,22 @@ _lib = None
 
 
 def load():
-    """dlopen the in-tree library (building it first if the source is newer and nvcc exists)."""
+    """dlopen the in-tree library.  Never compiles: `python -m vcs_h264_b200.build` (or
+    __graft_entry__.build()) does that; a missing library is an error, a stale one a warning."""
     global _lib
     if _lib is not None:
         return _lib
-    from . import build as _build
     path = os.environ.get("VCS_B200_LIB")   # A/B builds of the same sources (tools/ab_me.sh); normally unset
     if not path:
         path = LIB_PATH
-        if not os.path.exists(LIB_PATH) or (_build.stale() and os.path.exists(_build.NVCC)):
-            _build.build()               # in-tree, next to this file; raises if nvcc fails
+        if not os.path.exists(LIB_PATH):
+            raise OSError(f"{LIB_PATH} is missing: build it with `python -m vcs_h264_b200.build` "
+                          "(nvcc, sm_100a); this package has no CPU path")
+        from . import build as _build
+        if _build.stale():
+            import warnings
+            warnings.warn("libvcs_b200.so is older than its sources: run `python -m vcs_h264_b200.build`",
+                          RuntimeWarning, stacklevel=2)
     lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError = header/library mismatch: be loud

@@ -44,7 +44,8 @@ class ClipEncoder:
         self.N = _capi.num_blocks(H, W, block_size)
         self.coef_mode = coef_mode
         self.device = device
-        self.ctx = get_context(device)
+        # own context: its Q tables, stream and scratch are not shared with other front-ends on the device
+        self.ctx = _capi.Context(device)
         self.Q = _capi.q_tables(qf)
         self.ctx.set_q(self.Q)
 
@@ -78,7 +79,6 @@ class ClipEncoder:
             raise ValueError(f"frames must be [T,{self.H},{self.W},3] uint8")
         if out is None:
             out = self.alloc_host_outputs(T, want_coef, want_recon, pinned=False)
-        self.ctx.set_q(self.Q)
         self.ctx.call("vcs_encode_clip_host", self.params, _capi.ptr(frames), T, self.gop_len,
                       self.coef_mode, _capi.ptr(out["mv"]), _capi.ptr(out.get("cost")),
                       _capi.ptr(out.get("flags")), _capi.ptr(out.get("coef")),
@@ -106,11 +106,14 @@ class ClipEncoder:
         import torch
         T = int(frames_dev.shape[0])
         s = stream if stream is not None else torch.cuda.current_stream(frames_dev.device)
-        self.ctx.set_stream(s.cuda_stream)
-        self.ctx.call("vcs_encode_clip_dev", self.params, _capi.ptr(frames_dev), T, self.gop_len,
-                      self.coef_mode, _capi.ptr(out["mv"]), _capi.ptr(out.get("cost")),
-                      _capi.ptr(out.get("flags")), _capi.ptr(out.get("coef")),
-                      _capi.ptr(out.get("recon")))
+        self.ctx.set_stream(s.cuda_stream)        # borrowed for this call only: the handle may not outlive it
+        try:
+            self.ctx.call("vcs_encode_clip_dev", self.params, _capi.ptr(frames_dev), T, self.gop_len,
+                          self.coef_mode, _capi.ptr(out["mv"]), _capi.ptr(out.get("cost")),
+                          _capi.ptr(out.get("flags")), _capi.ptr(out.get("coef")),
+                          _capi.ptr(out.get("recon")))
+        finally:
+            self.ctx.use_own_stream()
         return out
 
     def me_device(self, frames_dev, out, stream=None):
@@ -119,8 +122,11 @@ class ClipEncoder:
         T = int(frames_dev.shape[0])
         s = stream if stream is not None else torch.cuda.current_stream(frames_dev.device)
         self.ctx.set_stream(s.cuda_stream)
-        self.ctx.call("vcs_me_search_clip_dev", self.params, _capi.ptr(frames_dev), T, self.gop_len,
-                      _capi.ptr(out["mv"]), _capi.ptr(out.get("cost")), _capi.ptr(out.get("flags")))
+        try:
+            self.ctx.call("vcs_me_search_clip_dev", self.params, _capi.ptr(frames_dev), T, self.gop_len,
+                          _capi.ptr(out["mv"]), _capi.ptr(out.get("cost")), _capi.ptr(out.get("flags")))
+        finally:
+            self.ctx.use_own_stream()
         return out
 
 
@@ -131,8 +137,9 @@ class ClipDecoder:
     def __init__(self, shape, block_size=16, gop_len=4, qf=50.0, coef_mode=_capi.COEF_I16_RINT, device=0):
         self.H, self.W, self.bs, self.gop_len = int(shape[0]), int(shape[1]), block_size, gop_len
         self.coef_mode, self.device = coef_mode, device
-        self.ctx = get_context(device)
+        self.ctx = _capi.Context(device)           # own context, like ClipEncoder
         self.Q = _capi.q_tables(qf)
+        self.ctx.set_q(self.Q)
 
     def decode_host(self, ref_frames, mv, coef, T):
         """ref_frames uint8 [nG,H,W,3] (the I-frames), mv int16 [nP,N,2], coef [nP,3,H,W] -> uint8 [nP,H,W,3]."""
@@ -141,7 +148,6 @@ class ClipDecoder:
         coef = np.ascontiguousarray(np.asarray(coef), COEF_DTYPES[self.coef_mode])
         ref_frames = np.ascontiguousarray(np.asarray(ref_frames), np.uint8)
         out = np.empty((nP, self.H, self.W, 3), np.uint8)
-        self.ctx.set_q(self.Q)
         self.ctx.call("vcs_decode_clip_host", self.H, self.W, self.bs, ref_frames.ctypes.data, T, self.gop_len,
                       mv.ctypes.data, self.coef_mode, coef.ctypes.data, out.ctypes.data)
         return out
@@ -150,9 +156,11 @@ class ClipDecoder:
         import torch
         s = stream if stream is not None else torch.cuda.current_stream(recon_dev.device)
         self.ctx.set_stream(s.cuda_stream)
-        self.ctx.set_q(self.Q)
-        self.ctx.call("vcs_decode_clip_dev", self.H, self.W, self.bs, _capi.ptr(ref_frames_dev), T, self.gop_len,
-                      _capi.ptr(mv_dev), self.coef_mode, _capi.ptr(coef_dev), _capi.ptr(recon_dev))
+        try:
+            self.ctx.call("vcs_decode_clip_dev", self.H, self.W, self.bs, _capi.ptr(ref_frames_dev), T, self.gop_len,
+                          _capi.ptr(mv_dev), self.coef_mode, _capi.ptr(coef_dev), _capi.ptr(recon_dev))
+        finally:
+            self.ctx.use_own_stream()
         return recon_dev
 
 

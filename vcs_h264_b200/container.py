@@ -47,6 +47,17 @@ def pack(i_frames, mv, coef, *, T, block_size, gop_len, coef_mode, qf=50.0, Q=No
     return b"".join([hdr, Q.tobytes(), i_frames.tobytes(), mv.tobytes(), coef.tobytes()])
 
 
+def check_mv_range(mv, H, W, bs):
+    """Every vector must keep its macroblock inside the frame (the reference's MC copy would raise otherwise,
+    motion.py:62-65); a container from the wire is not trusted."""
+    nbx = W // bs
+    k = np.arange(mv.shape[-2])
+    x = (k % nbx) * bs + mv[..., 0].astype(np.int32)
+    y = (k // nbx) * bs + mv[..., 1].astype(np.int32)
+    if mv.size and (x.min() < 0 or y.min() < 0 or x.max() > W - bs or y.max() > H - bs):
+        raise ValueError("container holds a motion vector that points outside the frame")
+
+
 def unpack(buf) -> dict:
     """Inverse of pack(): dict(T, H, W, block_size, gop_len, coef_mode, qf, Q, i_frames, mv, coef) -- arrays are views."""
     buf = memoryview(buf)
@@ -66,6 +77,8 @@ def unpack(buf) -> dict:
     for n in sizes:
         parts.append(buf[off:off + n])
         off += n
+    mv = np.frombuffer(parts[2], np.int16).reshape(n_p, N, 2)
+    check_mv_range(mv, H, W, bs)
     return dict(T=T, H=H, W=W, block_size=bs, gop_len=gop, coef_mode=cm, qf=qf,
                 Q=np.frombuffer(parts[0], np.float64).reshape(3, 8, 8),
                 i_frames=np.frombuffer(parts[1], np.uint8).reshape(n_i, H, W, 3),

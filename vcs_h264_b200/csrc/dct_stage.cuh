@@ -67,6 +67,7 @@ struct DctArgs {
     void *coef;              // [nP][3][H][W] output (forward) or input (inverse-only); may be null
     const uint8_t *pred_in;  // inverse-only: optional pred image to add (decoder.py:57)
     uint8_t *recon;          // [nP][H][W][3] or nullptr
+    int *err;                // mapped host flag: set when a motion vector points outside the frame
 };
 
 // 24 bytes (8 BGR pixels) starting at an arbitrary byte address, as 6 words
@@ -158,7 +159,11 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     const int mbx = bs_shift >= 0 ? x >> bs_shift : x / bs, mby = bs_shift >= 0 ? y >> bs_shift : y / bs;
                     if (mbx < nbx && mby < nby) {   // uncovered border stays 0 (motion.py:45-46)
                         const int16_t *m = mv + 2 * (mby * nbx + mbx);
-                        load24(ref + ((size_t)(y + m[1]) * W + (x + m[0])) * 3, pw);
+                        const int sx = x + m[0], sy = y + m[1];
+                        // a vector that leaves the frame (corrupt or foreign input; the reference would raise,
+                        // motion.py:62-65) is never followed: zero prediction, and the host is told
+                        if (sx >= 0 && sy >= 0 && sx + 8 <= W && sy < H) load24(ref + ((size_t)sy * W + sx) * 3, pw);
+                        else if (a.err) *(volatile int *)a.err = 1;
                     }
                 } else {             // per-pixel gather (block sizes that are not multiples of 8)
                     for (int u = 0; u < 8; ++u) {
@@ -166,8 +171,11 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                         uint32_t b3 = 0;
                         if (mbx < nbx && mby < nby) {
                             const int16_t *m = mv + 2 * (mby * nbx + mbx);
-                            const uint8_t *rp = ref + ((size_t)(y + m[1]) * W + (x + u + m[0])) * 3;
-                            b3 = (uint32_t)__ldg(rp) | ((uint32_t)__ldg(rp + 1) << 8) | ((uint32_t)__ldg(rp + 2) << 16);
+                            const int sx = x + u + m[0], sy = y + m[1];
+                            if (sx >= 0 && sy >= 0 && sx < W && sy < H) {
+                                const uint8_t *rp = ref + ((size_t)sy * W + sx) * 3;
+                                b3 = (uint32_t)__ldg(rp) | ((uint32_t)__ldg(rp + 1) << 8) | ((uint32_t)__ldg(rp + 2) << 16);
+                            } else if (a.err) *(volatile int *)a.err = 1;
                         }
                         for (int e = 0; e < 3; ++e) s_pred[(g_r * DCT_TILE_W + g_c + u) * 3 + e] = (uint8_t)(b3 >> (8 * e));
                     }
@@ -428,10 +436,34 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
 }
 
 // MotionProcessor.reconstruct_from_motion_vectors (motion.py:42-69) as its own kernel, for the
-// drop-in method; the fused path above never materialises pred.
+// drop-in method; the fused path above never materialises pred.  One thread = 4 pixels = 12 bytes = 3 aligned
+// words of the output row (W % 4 == 0 fast path: a 4-pixel group never straddles a macroblock when bs % 4 == 0).
 __global__ void mc_kernel(const uint8_t *__restrict__ ref, const int16_t *__restrict__ mv, int H,
-                          int W, int bs, int nbx, int nby, uint8_t *__restrict__ pred) {
+                          int W, int bs, int nbx, int nby, uint8_t *__restrict__ pred, int *err) {
     const size_t npix = (size_t)H * W;
+    if ((W & 3) == 0 && (bs & 3) == 0 && (reinterpret_cast<uintptr_t>(pred) & 3) == 0) {
+        const size_t ngrp = npix / 4;
+        for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < ngrp; k += (size_t)gridDim.x * blockDim.x) {
+            const int y = (int)(k / (W / 4)), x = (int)(k - (size_t)y * (W / 4)) * 4;
+            const int mbx = x / bs, mby = y / bs;
+            uint32_t w[3] = {0, 0, 0};
+            if (mbx < nbx && mby < nby) {
+                const int16_t *m = mv + 2 * (mby * nbx + mbx);
+                const int sx = x + m[0], sy = y + m[1];
+                if (sx >= 0 && sy >= 0 && sx + 4 <= W && sy < H) {
+                    const uint8_t *rp = ref + ((size_t)sy * W + sx) * 3;
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(rp);
+                    const uint32_t *q = reinterpret_cast<const uint32_t *>(a & ~uintptr_t(3));
+                    const int sh = (int)(a & 3) * 8;
+                    const uint32_t r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = sh ? __ldg(q + 3) : 0u;
+                    w[0] = __funnelshift_r(r0, r1, sh); w[1] = __funnelshift_r(r1, r2, sh); w[2] = __funnelshift_r(r2, r3, sh);
+                } else if (err) *(volatile int *)err = 1;
+            }
+            uint32_t *o = reinterpret_cast<uint32_t *>(pred + 12 * k);
+            o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+        }
+        return;
+    }
     for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < npix;
          k += (size_t)gridDim.x * blockDim.x) {
         const int y = (int)(k / W), x = (int)(k - (size_t)y * W);
@@ -439,8 +471,11 @@ __global__ void mc_kernel(const uint8_t *__restrict__ ref, const int16_t *__rest
         uint8_t b = 0, g = 0, r = 0;
         if (mbx < nbx && mby < nby) {
             const int16_t *m = mv + 2 * (mby * nbx + mbx);
-            const uint8_t *rp = ref + ((size_t)(y + m[1]) * W + (x + m[0])) * 3;
-            b = rp[0]; g = rp[1]; r = rp[2];
+            const int sx = x + m[0], sy = y + m[1];
+            if (sx >= 0 && sy >= 0 && sx < W && sy < H) {
+                const uint8_t *rp = ref + ((size_t)sy * W + sx) * 3;
+                b = rp[0]; g = rp[1]; r = rp[2];
+            } else if (err) *(volatile int *)err = 1;
         }
         pred[3 * k] = b; pred[3 * k + 1] = g; pred[3 * k + 2] = r;
     }
@@ -461,13 +496,53 @@ __global__ void count_nonzero_kernel(const void *__restrict__ coef, size_t n, un
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
-// get_residuals (motion.py:38-40) / _fully_reconstruct (decoder.py:57): byte-wise wrap
+// get_residuals (motion.py:38-40) / _fully_reconstruct (decoder.py:57): byte-wise wrap, 16 bytes per thread
+// when the three pointers are 16-byte aligned (__vsub4 / __vadd4 on each word), byte-wise otherwise and for the tail.
 template <int ADD>
 __global__ void wrap_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, size_t n,
                             uint8_t *__restrict__ out) {
-    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n;
+    size_t done = 0;
+    if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        const size_t nv = n / 16;
+        const uint4 *av = reinterpret_cast<const uint4 *>(a), *bv = reinterpret_cast<const uint4 *>(b);
+        uint4 *ov = reinterpret_cast<uint4 *>(out);
+        for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nv; k += (size_t)gridDim.x * blockDim.x) {
+            const uint4 x = __ldg(av + k), y = __ldg(bv + k);
+            ov[k] = ADD ? make_uint4(__vadd4(x.x, y.x), __vadd4(x.y, y.y), __vadd4(x.z, y.z), __vadd4(x.w, y.w))
+                        : make_uint4(__vsub4(x.x, y.x), __vsub4(x.y, y.y), __vsub4(x.z, y.z), __vsub4(x.w, y.w));
+        }
+        done = nv * 16;
+    }
+    for (size_t k = done + blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n;
          k += (size_t)gridDim.x * blockDim.x)
         out[k] = ADD ? (uint8_t)(a[k] + b[k]) : (uint8_t)(a[k] - b[k]);
+}
+
+// DCTCompressor._dct2 / _idct2 (DCTcompressor.py:111-121) on bare 8x8 float64 blocks: C.X.C^T or C^T.X.C as two
+// products of sequential-k FMA chains (what np.matmul does for these shapes).  One thread per
+// output element; the private helpers of the class surface call this, the hot path uses dct_stage_kernel.
+__global__ void dct2_blocks_kernel(const double *__restrict__ in, int nblocks, int inverse, double *__restrict__ out) {
+    __shared__ double sx[4][64], st[4][64];
+    const int t = threadIdx.x & 63, lb = threadIdx.x >> 6, i = t >> 3, j = t & 7;
+    for (int b0 = blockIdx.x * 4; b0 < nblocks; b0 += gridDim.x * 4) {
+        const int b = b0 + lb;
+        if (b < nblocks) sx[lb][t] = in[(size_t)b * 64 + t];
+        __syncthreads();
+        if (b < nblocks) {
+            double s = 0.0;   // T = C.X (forward) or C^T.X (inverse)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = __fma_rn(inverse ? c_dct[k * 8 + i] : c_dct[i * 8 + k], sx[lb][k * 8 + j], s);
+            st[lb][t] = s;
+        }
+        __syncthreads();
+        if (b < nblocks) {
+            double s = 0.0;   // T.C^T (forward) or T.C (inverse)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = __fma_rn(st[lb][i * 8 + k], inverse ? c_dct[k * 8 + j] : c_dct[j * 8 + k], s);
+            out[(size_t)b * 64 + t] = s;
+        }
+        __syncthreads();
+    }
 }
 
 }  // namespace vcs

@@ -28,6 +28,8 @@ microbench_kernel(uint32_t *out, int iters, uint32_t seed, long long *cycles) {
     s_buf[threadIdx.x + MB_THREADS] = b;
     __syncthreads();
     long long t0, t1;
+    unsigned long long g0, g1;   // nanoseconds: SM clock = clock64 span / globaltimer span of the SAME block
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0) :: "memory");
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t0) :: "memory");
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -64,11 +66,12 @@ microbench_kernel(uint32_t *out, int iters, uint32_t seed, long long *cycles) {
         }
     }
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t1) :: "memory");
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1) :: "memory");
     uint32_t s = 0;
 #pragma unroll
     for (int j = 0; j < MB_ACC; ++j) s ^= acc[j];
     out[blockIdx.x * MB_THREADS + threadIdx.x] = s + a;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *cycles = t1 - t0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { cycles[0] = t1 - t0; cycles[1] = (long long)(g1 - g0); }
 }
 
 }  // namespace vcs

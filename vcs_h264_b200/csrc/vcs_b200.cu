@@ -53,6 +53,8 @@ struct vcs_ctx {
     std::vector<EvTriple> ev_pool;
     size_t ev_used = 0;
     MeTiledState tiled;
+    int *h_errflag = nullptr;          // pinned, mapped: kernels store 1 when a motion vector leaves the frame
+    uint64_t q_version = 0;
 };
 
 namespace {
@@ -66,6 +68,33 @@ int fail(vcs_ctx *ctx, int code, const char *fmt, ...) {
     }
     return code;
 }
+
+// Every entry point runs with the context's device current and puts the caller's device back on return
+// (torch and other contexts in the same process keep theirs).
+struct DevGuard {
+    int prev = -1, dev;
+    explicit DevGuard(int d) : dev(d) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DevGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+
+// A kernel that met a motion vector pointing outside the frame wrote zero prediction there and raised the flag;
+// the next call on the context (or vcs_synchronize) reports it once.
+int pending_device_error(vcs_ctx *ctx) {
+    if (ctx->h_errflag && *(volatile int *)ctx->h_errflag) {
+        *(volatile int *)ctx->h_errflag = 0;
+        return fail(ctx, VCS_E_INVALID, "an earlier launch met a motion vector pointing outside the frame "
+                                        "(the prediction was zero-filled there)");
+    }
+    return VCS_OK;
+}
+
+#define VCS_ENTER(ctx)                                       \
+    if (!(ctx)) return VCS_E_INVALID;                        \
+    DevGuard dev_guard__((ctx)->device);                     \
+    do { int rc__ = pending_device_error(ctx); if (rc__) return rc__; } while (0)
 
 #define CK(ctx, call)                                                                          \
     do {                                                                                       \
@@ -201,6 +230,7 @@ int launch_dct(vcs_ctx *ctx, cudaStream_t st, DctArgs &a, int nP) {
         }
     }
     a.Q = ctx->d_Q;
+    a.err = ctx->h_errflag;
     // persistent warps: 4 CTAs of 4 warps per SM, each warp walks 8x32-pixel tiles
     const long long nitems = (long long)((a.W + DCT_TILE_W - 1) / DCT_TILE_W) * (a.H / 8) * nP;
     if (nitems >= (1ll << 31)) return fail(ctx, VCS_E_INVALID, "too many 8x32 tiles in one launch (%lld)", nitems);
@@ -255,7 +285,7 @@ int run_mb(vcs_ctx *ctx, int iters, double *rate, double *mhz) {
     const int blocks = ctx->sm_count * 8;
     uint32_t *d_out; long long *d_cyc; int rc;
     if ((rc = dev_buf(ctx, S_MB, (size_t)blocks * MB_THREADS * 4, (void **)&d_out))) return rc;
-    if ((rc = dev_buf(ctx, S_CYC, 8, (void **)&d_cyc))) return rc;
+    if ((rc = dev_buf(ctx, S_CYC, 16, (void **)&d_cyc))) return rc;
     cudaEvent_t e0, e1;
     CK(ctx, cudaEventCreate(&e0));
     CK(ctx, cudaEventCreate(&e1));
@@ -269,8 +299,8 @@ int run_mb(vcs_ctx *ctx, int iters, double *rate, double *mhz) {
     ctx->launches += 2;
     float ms;
     CK(ctx, cudaEventElapsedTime(&ms, e0, e1));
-    long long cyc = 0;
-    CK(ctx, cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+    long long cyc[2] = {0, 0};   // block 0: SM clocks and globaltimer nanoseconds over its own loop
+    CK(ctx, cudaMemcpy(cyc, d_cyc, 16, cudaMemcpyDeviceToHost));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     const double warps = (double)blocks * MB_THREADS / 32.0;
@@ -278,7 +308,7 @@ int run_mb(vcs_ctx *ctx, int iters, double *rate, double *mhz) {
     if (W == 5) ops /= 3.0;  // report words/s/32 for the wrap8 triple
     if (W == 6) ops = warps * (double)iters * MB_ACC * MB_UNROLL;  // count the VABSDIFF4s only
     if (rate) *rate = ops / (ms * 1e-3);
-    if (mhz) *mhz = (double)cyc / (ms * 1e3);
+    if (mhz) *mhz = cyc[1] > 0 ? (double)cyc[0] / ((double)cyc[1] * 1e-3) : 0.0;
     return VCS_OK;
 }
 
@@ -361,47 +391,45 @@ int vcs_create(int device, vcs_ctx **out) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return VCS_E_CUDA;  // no CPU fallback
+    DevGuard guard(device);             // the caller's current device is restored on return
     vcs_ctx *ctx = new vcs_ctx();
     ctx->device = device;
     cudaDeviceProp prop;
-    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
         delete ctx;
         return VCS_E_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
-    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&ctx->d_Q, sizeof(ctx->h_Q)) != cudaSuccess) {
-        delete ctx;
-        return VCS_E_CUDA;
-    }
-    ctx->stream = ctx->own_stream;
     double C[64];
     vcs_dct_matrix(C);
     static_assert(DCT_SMEM_BYTES <= 48 * 1024, "dct_stage_kernel relies on the default shared-memory limit");
-    if (cudaMemcpyToSymbol(c_dct, C, sizeof(C)) != cudaSuccess) {
-        delete ctx;
-        return VCS_E_CUDA;
-    }
     vcs_q_tables(50.0, ctx->h_Q);  // DCTcompressor.py:29 QF = 50
-    if (cudaMemcpy(ctx->d_Q, ctx->h_Q, sizeof(ctx->h_Q), cudaMemcpyHostToDevice) != cudaSuccess) {
-        delete ctx;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&ctx->d_Q, sizeof(ctx->h_Q)) != cudaSuccess ||
+        cudaHostAlloc((void **)&ctx->h_errflag, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaMemcpyToSymbol(c_dct, C, sizeof(C)) != cudaSuccess ||
+        cudaMemcpy(ctx->d_Q, ctx->h_Q, sizeof(ctx->h_Q), cudaMemcpyHostToDevice) != cudaSuccess) {
+        vcs_destroy(ctx);
         return VCS_E_CUDA;
     }
+    *ctx->h_errflag = 0;
+    ctx->stream = ctx->own_stream;
     *out = ctx;
     return VCS_OK;
 }
 
 int vcs_destroy(vcs_ctx *ctx) {
     if (!ctx) return VCS_OK;
-    cudaSetDevice(ctx->device);
+    DevGuard guard(ctx->device);
     cudaDeviceSynchronize();
     for (int s = 0; s < NUM_DEV_SLOTS; ++s)
         if (ctx->dev[s]) cudaFree(ctx->dev[s]);
     if (ctx->d_Q) cudaFree(ctx->d_Q);
+    if (ctx->h_errflag) cudaFreeHost(ctx->h_errflag);
     for (auto &t : ctx->ev_pool) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
     for (auto &e : ctx->chunk_events) cudaEventDestroy(e);
     me_tiled_destroy(ctx->tiled);
@@ -425,9 +453,9 @@ int vcs_use_own_stream(vcs_ctx *ctx) {
 }
 
 int vcs_synchronize(vcs_ctx *ctx) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    return VCS_OK;
+    return pending_device_error(ctx);
 }
 
 int vcs_device_info(vcs_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin) {
@@ -445,6 +473,8 @@ int vcs_set_q(vcs_ctx *ctx, const double *Q) {
     if (!ctx || !Q) return VCS_E_INVALID;
     for (int k = 0; k < 192; ++k)
         if (!(Q[k] != 0.0)) return fail(ctx, VCS_E_INVALID, "Q[%d] is zero or NaN", k);
+    if (memcmp(ctx->h_Q, Q, sizeof(ctx->h_Q)) == 0) return VCS_OK;   // unchanged: nothing to upload
+    ctx->q_version += 1;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(ctx->h_Q, Q, sizeof(ctx->h_Q));
     CK(ctx, cudaMemcpy(ctx->d_Q, ctx->h_Q, sizeof(ctx->h_Q), cudaMemcpyHostToDevice));
@@ -454,14 +484,14 @@ int vcs_set_q(vcs_ctx *ctx, const double *Q) {
 // ---- motion estimation -------------------------------------------------------------------
 int vcs_me_search_dev(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *cur, const uint8_t *ref,
                       int16_t *mv, uint32_t *cost, uint8_t *flags) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!cur || !ref) return fail(ctx, VCS_E_INVALID, "frame pointer is NULL");
     return launch_me(ctx, ctx->stream, p, pair_addr(cur, ref), 1, mv, cost, flags);
 }
 
 int vcs_me_search_clip_dev(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T,
                            int gop_len, int16_t *mv, uint32_t *cost, uint8_t *flags) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!frames || !p || gop_len < 2 || T < 1) return fail(ctx, VCS_E_INVALID, "bad clip arguments");
     return launch_me(ctx, ctx->stream, p, clip_addr(frames, p->H, p->W, gop_len),
                      vcs_num_p_frames(T, gop_len), mv, cost, flags);
@@ -469,7 +499,7 @@ int vcs_me_search_clip_dev(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *
 
 int vcs_me_search_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *cur, const uint8_t *ref,
                        int16_t *mv, uint32_t *cost, uint8_t *flags) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     int rc = check_me_params(ctx, p);
     if (rc) return rc;
     if (!cur || !ref || !mv) return fail(ctx, VCS_E_INVALID, "NULL argument");
@@ -493,19 +523,19 @@ int vcs_me_search_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *cur,
 
 // ---- MC / wrap arithmetic ------------------------------------------------------------------
 int vcs_mc_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref, const int16_t *mv, uint8_t *pred) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!ref || !mv || !pred || bs <= 0 || H < bs || W < bs) return fail(ctx, VCS_E_INVALID, "bad MC arguments");
     const size_t npix = (size_t)H * W;
     int blocks = (int)((npix + 255) / 256);
     if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-    mc_kernel<<<blocks, 256, 0, ctx->stream>>>(ref, mv, H, W, bs, W / bs, H / bs, pred);
+    mc_kernel<<<blocks, 256, 0, ctx->stream>>>(ref, mv, H, W, bs, W / bs, H / bs, pred, ctx->h_errflag);
     CK(ctx, cudaGetLastError());
     ctx->launches += 1;
     return VCS_OK;
 }
 
 int vcs_mc_host(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref, const int16_t *mv, uint8_t *pred) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!ref || !mv || !pred || bs <= 0 || H < bs || W < bs) return fail(ctx, VCS_E_INVALID, "bad MC arguments");
     const size_t fs = (size_t)H * W * 3;
     const int N = vcs_num_blocks(H, W, bs);
@@ -528,7 +558,7 @@ int vcs_mc_host(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref, const in
 }
 
 static int wrap_dev(vcs_ctx *ctx, int add, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!a || !b || !out) return fail(ctx, VCS_E_INVALID, "NULL argument");
     if (n == 0) return VCS_OK;
     int blocks = (int)((n + 255) / 256);
@@ -541,7 +571,7 @@ static int wrap_dev(vcs_ctx *ctx, int add, const uint8_t *a, const uint8_t *b, s
 }
 
 static int wrap_host(vcs_ctx *ctx, int add, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!a || !b || !out) return fail(ctx, VCS_E_INVALID, "NULL argument");
     if (n == 0) return VCS_OK;
     uint8_t *d; int rc;
@@ -562,7 +592,7 @@ int vcs_add_wrap_host(vcs_ctx *c, const uint8_t *a, const uint8_t *b, size_t n, 
 
 // ---- DCT stage -------------------------------------------------------------------------------
 int vcs_compress_dev(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, int coef_mode, void *coef) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!bgr || !coef) return fail(ctx, VCS_E_INVALID, "NULL argument");
     DctArgs a;
     memset(&a, 0, sizeof(a));
@@ -571,7 +601,7 @@ int vcs_compress_dev(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, int coef_mo
 }
 
 int vcs_compress_host(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, int coef_mode, void *coef) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!bgr || !coef) return fail(ctx, VCS_E_INVALID, "NULL argument");
     if (H <= 0 || W <= 0 || H % 8 || W % 8 || coef_mode < 0 || coef_mode > 3)
         return fail(ctx, VCS_E_INVALID, "H=%d W=%d must be multiples of 8; coef_mode=%d", H, W, coef_mode);
@@ -589,7 +619,7 @@ int vcs_compress_host(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, int coef_m
 
 int vcs_decompress_dev(vcs_ctx *ctx, int H, int W, int coef_mode, const void *coef, const uint8_t *pred,
                        uint8_t *bgr) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!coef || !bgr) return fail(ctx, VCS_E_INVALID, "NULL argument");
     DctArgs a;
     memset(&a, 0, sizeof(a));
@@ -600,7 +630,7 @@ int vcs_decompress_dev(vcs_ctx *ctx, int H, int W, int coef_mode, const void *co
 
 int vcs_decompress_host(vcs_ctx *ctx, int H, int W, int coef_mode, const void *coef, const uint8_t *pred,
                         uint8_t *bgr) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!coef || !bgr) return fail(ctx, VCS_E_INVALID, "NULL argument");
     if (H <= 0 || W <= 0 || H % 8 || W % 8 || coef_mode < 0 || coef_mode > 3)
         return fail(ctx, VCS_E_INVALID, "H=%d W=%d must be multiples of 8; coef_mode=%d", H, W, coef_mode);
@@ -618,10 +648,30 @@ int vcs_decompress_host(vcs_ctx *ctx, int H, int W, int coef_mode, const void *c
     return VCS_OK;
 }
 
+// DCTCompressor._dct2 / _idct2 (DCTcompressor.py:111-121) on n bare 8x8 float64 blocks (host buffers)
+int vcs_dct2_blocks_host(vcs_ctx *ctx, int nblocks, int inverse, const double *in, double *out) {
+    VCS_ENTER(ctx);
+    if (!in || !out || nblocks < 0) return fail(ctx, VCS_E_INVALID, "bad dct2 arguments");
+    if (nblocks == 0) return VCS_OK;
+    const size_t bytes = (size_t)nblocks * 64 * sizeof(double);
+    double *d; int rc;
+    if ((rc = dev_buf(ctx, S_COEF, 2 * bytes, (void **)&d))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(d, in, bytes, cudaMemcpyHostToDevice, st));
+    int blocks = (nblocks + 3) / 4;
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    dct2_blocks_kernel<<<blocks, 256, 0, st>>>(d, nblocks, inverse != 0, d + (size_t)nblocks * 64);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    CK(ctx, cudaMemcpyAsync(out, d + (size_t)nblocks * 64, bytes, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return VCS_OK;
+}
+
 // ---- fused clip paths ------------------------------------------------------------------------
 int vcs_residual_dct_clip_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *frames, int T, int gop_len,
                               const int16_t *mv, int coef_mode, void *coef, uint8_t *recon) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!frames || !mv || gop_len < 2 || T < 1 || bs <= 0 || H < bs || W < bs)
         return fail(ctx, VCS_E_INVALID, "bad clip arguments");
     DctArgs a;
@@ -636,7 +686,7 @@ int vcs_residual_dct_clip_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t 
 // IDCT + truncating store + YCrCb->BGR + wrap add, one launch.
 int vcs_decode_clip_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_frames, int T, int gop_len,
                         const int16_t *mv, int coef_mode, const void *coef, uint8_t *recon) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!ref_frames || !mv || !coef || !recon || gop_len < 2 || T < 1 || bs <= 0 || H < bs || W < bs)
         return fail(ctx, VCS_E_INVALID, "bad decode arguments");
     const long long fs = (long long)H * W * 3;
@@ -651,7 +701,7 @@ int vcs_decode_clip_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_f
 
 int vcs_decode_clip_host(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_frames, int T, int gop_len,
                          const int16_t *mv, int coef_mode, const void *coef, uint8_t *recon) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!ref_frames || !mv || !coef || !recon || gop_len < 2 || T < 1 || bs <= 0 || H < bs || W < bs)
         return fail(ctx, VCS_E_INVALID, "bad decode arguments");
     if (H % 8 || W % 8 || coef_mode < 0 || coef_mode > 3)
@@ -682,7 +732,7 @@ int vcs_decode_clip_host(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_
 
 // numerator of dct.py:188-191's sparsity: number of non-zero coefficients in n elements (device pointer)
 int vcs_count_nonzero_dev(vcs_ctx *ctx, int coef_mode, const void *coef, size_t n, unsigned long long *count_host) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!coef || !count_host || coef_mode < 0 || coef_mode > 3) return fail(ctx, VCS_E_INVALID, "bad arguments");
     unsigned long long *d_cnt; int rc;
     if ((rc = dev_buf(ctx, S_CYC, 8, (void **)&d_cnt))) return rc;
@@ -705,7 +755,7 @@ int vcs_count_nonzero_dev(vcs_ctx *ctx, int coef_mode, const void *coef, size_t 
 int vcs_encode_clip_dev(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
                         int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef,
                         uint8_t *recon) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (!frames || !p || gop_len < 2 || T < 1) return fail(ctx, VCS_E_INVALID, "bad clip arguments");
     return encode_dev(ctx, ctx->stream, p, clip_addr(frames, p->H, p->W, gop_len),
                       vcs_num_p_frames(T, gop_len), coef_mode, mv, cost, flags, coef, recon);
@@ -714,7 +764,7 @@ int vcs_encode_clip_dev(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fra
 int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
                          int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef,
                          uint8_t *recon) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     int rc = check_me_params(ctx, p);
     if (rc) return rc;
     if (!frames || gop_len < 2 || T < 1) return fail(ctx, VCS_E_INVALID, "bad clip arguments");
@@ -790,6 +840,7 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
     // (Running consecutive searches on two streams so that one fills the other's tail was tried and is slower:
     // the persistent search CTAs of the next chunk then keep the DCT stage of this chunk off the SMs.)
     cudaStream_t sc = ctx->stream;
+    auto pipeline = [&]() -> int {
     int uploaded = 0, p0 = 0;
     for (int c = 0; c < nsegs; ++c) {                    // frames after the last P-frame are never needed on the device
         const int np = sizes[c];
@@ -829,9 +880,14 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
         }
         p0 += np;
     }
-    CK(ctx, cudaStreamSynchronize(ctx->s_d2h));
-    CK(ctx, cudaStreamSynchronize(sc));
     return VCS_OK;
+    };
+    rc = pipeline();
+    // success or not, nothing may still be reading or writing the caller's buffers when this returns
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(sc), e3 = cudaStreamSynchronize(ctx->s_d2h);
+    if (rc) return rc;
+    CK(ctx, e1); CK(ctx, e2); CK(ctx, e3);
+    return pending_device_error(ctx);
 }
 
 // ---- intra mode decision (IntraframeCompression/intraframe.py:24-317) ---------------------------
@@ -843,11 +899,13 @@ static int intra_check(vcs_ctx *ctx, int H, int W, int m, const void *a, const v
 }
 
 int vcs_intra_luma4x4_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, int32_t *res, int32_t *pred, uint8_t *modes) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     int rc = intra_check(ctx, H, W, 4, Y, modes);
     if (rc) return rc;
     if (!res || !pred || (W / 4 < 2 && H / 4 > 1))
         return fail(ctx, VCS_E_INVALID, "luma4x4 needs at least two block columns (the reference indexes column j+1)");
+    if (((uintptr_t)Y & 3) || (((uintptr_t)res | (uintptr_t)pred) & 15))
+        return fail(ctx, VCS_E_INVALID, "luma4x4: Y must be 4-byte aligned, res/pred 16-byte aligned");
     const int nb = (H / 4) * (W / 4);
     intra_luma4x4_kernel<<<(nb + 127) / 128, 128, 0, ctx->stream>>>(Y, H, W, res, pred, modes);
     CK(ctx, cudaGetLastError());
@@ -856,10 +914,12 @@ int vcs_intra_luma4x4_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, int32_t 
 }
 
 int vcs_intra_luma16x16_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, int32_t *res, int32_t *pred, uint8_t *modes) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     int rc = intra_check(ctx, H, W, 16, Y, modes);
     if (rc) return rc;
     if (!res || !pred) return fail(ctx, VCS_E_INVALID, "NULL argument");
+    if (((uintptr_t)Y & 7) || (((uintptr_t)res | (uintptr_t)pred) & 15))
+        return fail(ctx, VCS_E_INVALID, "luma16x16: Y must be 8-byte aligned, res/pred 16-byte aligned");
     const int nb = (H / 16) * (W / 16);
     intra_luma16x16_kernel<<<(nb * 32 + 255) / 256, 256, 0, ctx->stream>>>(Y, H, W, res, pred, modes);
     CK(ctx, cudaGetLastError());
@@ -869,7 +929,7 @@ int vcs_intra_luma16x16_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, int32_
 
 int vcs_intra_chroma8x8_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Cr, const uint8_t *Cb, int32_t *crres,
                             int32_t *crpred, int32_t *cbres, int32_t *cbpred, uint8_t *modes) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     int rc = intra_check(ctx, H, W, 8, Cr, Cb);
     if (rc) return rc;
     if (!crres || !crpred || !cbres || !cbpred || !modes) return fail(ctx, VCS_E_INVALID, "NULL argument");
@@ -884,7 +944,7 @@ int vcs_intra_chroma8x8_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Cr, const
 // which: 0 luma4x4, 1 luma16x16 (planes: Y), 2 chroma8x8 (planes: Cr then Cb).  Host buffers.
 int vcs_intra_host(vcs_ctx *ctx, int which, int H, int W, const uint8_t *p0, const uint8_t *p1, int32_t *res0,
                    int32_t *pred0, int32_t *res1, int32_t *pred1, uint8_t *modes) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (which < 0 || which > 2) return fail(ctx, VCS_E_INVALID, "which must be 0, 1 or 2");
     const int m = which == 0 ? 4 : (which == 1 ? 16 : 8);
     int rc = intra_check(ctx, H, W, m, p0, modes);
@@ -915,14 +975,14 @@ int vcs_intra_host(vcs_ctx *ctx, int which, int H, int W, const uint8_t *p0, con
 
 // ---- measurement support ---------------------------------------------------------------------
 int vcs_enable_kernel_timing(vcs_ctx *ctx, int on) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     ctx->timing = on != 0;
     ctx->ev_used = 0;
     return VCS_OK;
 }
 
 int vcs_kernel_times(vcs_ctx *ctx, double *me_ms_total, double *dct_ms_total, int *ncalls) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     CK(ctx, cudaDeviceSynchronize());
     double me = 0, dct = 0;
     for (size_t k = 0; k < ctx->ev_used; ++k) {
@@ -940,7 +1000,7 @@ int vcs_kernel_times(vcs_ctx *ctx, double *me_ms_total, double *dct_ms_total, in
 
 // ---- 4:2:0 chroma subsampling demo (ChromaSubsampling/chroma.py) ------------------------------------
 int vcs_chroma420_dev(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, uint8_t *Y, uint8_t *cr, uint8_t *cb) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (H <= 0 || W <= 0 || !bgr || !Y || !cr || !cb) return fail(ctx, VCS_E_INVALID, "bad chroma420 arguments");
     const dim3 block(32, 8), grid((W / 2 + 1 + 31) / 32, (H / 2 + 1 + 7) / 8);
     chroma420_kernel<<<grid, block, 0, ctx->stream>>>(bgr, H, W, Y, cr, cb);
@@ -951,7 +1011,7 @@ int vcs_chroma420_dev(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, uint8_t *Y
 
 int vcs_chroma420_to_bgr_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, const uint8_t *cr, const uint8_t *cb,
                              uint8_t *bgr) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (H <= 0 || W <= 0 || !bgr || !Y || !cr || !cb) return fail(ctx, VCS_E_INVALID, "bad chroma420 arguments");
     const size_t npix = (size_t)H * W;
     size_t blocks = (npix + 255) / 256;
@@ -965,7 +1025,7 @@ int vcs_chroma420_to_bgr_dev(vcs_ctx *ctx, int H, int W, const uint8_t *Y, const
 
 int vcs_chroma420_host(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, uint8_t *Y, uint8_t *cr, uint8_t *cb,
                        uint8_t *bgr_out) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (H <= 0 || W <= 0 || !bgr || !Y || !cr || !cb) return fail(ctx, VCS_E_INVALID, "bad chroma420 arguments");
     const size_t npix = (size_t)H * W, ns = (size_t)((H + 1) / 2) * ((W + 1) / 2);
     uint8_t *d_img, *d_pl, *d_out = nullptr;
@@ -987,7 +1047,7 @@ int vcs_chroma420_host(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, uint8_t *
 
 int vcs_chroma420_to_bgr_host(vcs_ctx *ctx, int H, int W, const uint8_t *Y, const uint8_t *cr, const uint8_t *cb,
                               uint8_t *bgr) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (H <= 0 || W <= 0 || !bgr || !Y || !cr || !cb) return fail(ctx, VCS_E_INVALID, "bad chroma420 arguments");
     const size_t npix = (size_t)H * W, ns = (size_t)((H + 1) / 2) * ((W + 1) / 2);
     uint8_t *d_pl, *d_out;
@@ -1005,7 +1065,7 @@ int vcs_chroma420_to_bgr_host(vcs_ctx *ctx, int H, int W, const uint8_t *Y, cons
 }
 
 int vcs_microbench(vcs_ctx *ctx, int which, int iters, double *warp_instr_per_s, double *sm_mhz) {
-    if (!ctx) return VCS_E_INVALID;
+    VCS_ENTER(ctx);
     if (iters <= 0) iters = 2000;
     switch (which) {
         case 0: return run_mb<0>(ctx, iters, warp_instr_per_s, sm_mhz);

@@ -7,11 +7,17 @@ from .motion import MotionProcessor
 WRITE_REF_FRAMES = True
 
 
+def _fourcc(code):
+    """cv2.VideoWriter_fourcc(*code) without needing OpenCV at construction time (same little-endian packing)."""
+    return sum(ord(c) << (8 * i) for i, c in enumerate(code))
+
+
 class Decoder:
     def __init__(self, encoded_frames, fps, shape, ref_frames, block_size, with_DCT, dct_block_size=None):
         self.encoded_frames = encoded_frames
         self.fps = fps
         self.shape = shape
+        self.fourcc = _fourcc('X264')                      # decoder.py:16
         self.ref_frames = ref_frames
         self.MotionProcessor = MotionProcessor(block_size=block_size, shape=shape)
         self.DCTCompressor = DCTCompressor(
@@ -32,7 +38,7 @@ class Decoder:
     def reconstruct_video(self, with_residuals):
         """decoder.py:23-47: writes output.mp4 in the cwd with fourcc X264."""
         import cv2
-        writer = cv2.VideoWriter('output.mp4', cv2.VideoWriter_fourcc(*'X264'), self.fps,
+        writer = cv2.VideoWriter('output.mp4', self.fourcc, self.fps,
                                  (self.shape[1], self.shape[0]))
         print("Set up video writer")
         frames = self.decode_frames(with_residuals)

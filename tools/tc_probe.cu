@@ -340,6 +340,95 @@ __global__ void __launch_bounds__(32 * (WORKERS + 1), 1) k_pipe(int iters, uint3
     if (warp == 0) tc_dealloc(tbase, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// part 3 (mode 20..): raw issue rate of small tcgen05.mma.kind::i8 -- NI issuing warps (one elected lane each, own
+// 128-column group: D at +0, A at +64), each issues `count` MMAs back to back, then one commit and a wait.
+// Answers: is a 128 x N x 32 MMA issue-bound (time independent of N) and do several issuers overlap?
+template <int N, int NI>
+__global__ void __launch_bounds__(128, 1) k_issue(int count, uint32_t *out, long long *cyc, uint32_t *status) {
+    __shared__ __align__(128) uint8_t sB[32 * 64];
+    __shared__ __align__(8) uint64_t bar[4];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 32 * 64; i += 128) sB[i] = 0;
+    __syncthreads();
+    if (tid < 32) {                                // word j (K bytes 4j..4j+3) -> column j
+        if (N >= 16) sB[tid * 16 + tid / 4] = 1;   // N-major, first 16-wide n group
+        else sB[(tid / 4) * 16 + (tid % 16) + (tid / 16) * 128] = 1;   // K-major, one 8-row n group
+    }
+    if (tid == 0) {
+        for (int g = 0; g < 4; ++g) mbar_init(&bar[g], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tc_alloc(&tmem_slot, 512);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    {   // every warp zeroes its lane quarter of all four groups' D and fills A
+        uint32_t z[16], a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { z[j] = 0; a[j] = hash32(tid * 16 + j + 1); }
+        for (int g = 0; g < 4; ++g) {
+            const uint32_t lb = tbase + ((uint32_t)(32 * warp) << 16) + 128u * g;
+            for (int c = 0; c < 64; c += 16) tc_st16(lb + c, z);
+            tc_st16(lb + 64, a);
+        }
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    long long t0 = clock64(), t1 = t0;
+    bool ok = true;
+    if (warp < NI && lane == 0) {
+        const uint32_t idesc = make_idesc(128, N, N >= 16 ? 1 : 0);
+        // N = 8 uses the K-major form (one n group): same bytes work because only n < 8 rows are read: (n%8)*16 + k%16 + (k/16)*128
+        const uint64_t desc = N >= 16 ? make_desc(smem_u32(sB), 128, 512) : make_desc(smem_u32(sB), 128, 256);
+        const uint32_t col = tbase + 128u * warp;
+        for (int i = 0; i < count; ++i) tc_mma_i8_ts(col, col + 64 + 8 * (i & 1), desc, idesc, 1);
+        tc_commit(&bar[warp]);
+        t1 = clock64();          // issue done
+        ok = mbar_wait(&bar[warp], 0);
+    }
+    const long long t2 = clock64();
+    if (warp < NI && lane == 0) { cyc[2 * warp] = t1 - t0; cyc[2 * warp + 1] = t2 - t0; }
+    if (!ok) atomicAdd(status, 1);
+    __syncthreads();
+    tc_fence_after();
+    uint32_t d[16];
+    tc_ld16(tbase + ((uint32_t)(32 * warp) << 16), d);
+    tc_wait_ld();
+    out[tid] = d[0] + d[7];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc_dealloc(tbase, 512);
+}
+
+template <int N, int NI>
+static int run_issue(int count) {
+    uint32_t *d_out, *d_status; long long *d_cyc;
+    CK(cudaMalloc(&d_out, 128 * 4)); CK(cudaMalloc(&d_cyc, 64)); CK(cudaMalloc(&d_status, 4));
+    CK(cudaMemset(d_status, 0, 4));
+    k_issue<N, NI><<<1, 128>>>(count / 4 + 1, d_out, d_cyc, d_status);
+    k_issue<N, NI><<<1, 128>>>(count, d_out, d_cyc, d_status);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    long long cyc[8]; uint32_t st, o[128];
+    CK(cudaMemcpy(cyc, d_cyc, 64, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&st, d_status, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(o, d_out, 512, cudaMemcpyDeviceToHost));
+    const uint32_t a0 = hash32(1), a8 = hash32(9);   // row 0: word 0 of buffer 0 and of buffer 1 (A + 8 columns)
+    auto bsum = [](uint32_t a) { return (a & 255) + ((a >> 8) & 255) + ((a >> 16) & 255) + (a >> 24); };
+    const uint32_t want0 = (uint32_t)((count + 1) / 2) * bsum(a0) + (uint32_t)(count / 2) * bsum(a8);
+    printf("issue N=%d issuers=%d count=%d: issue %.1f clk/MMA, complete %.1f clk/MMA per issuer (%.1f aggregate), timeouts %u, D[0][0] %s\n",
+           N, NI, count, (double)cyc[0] / count, (double)cyc[1] / count, (double)cyc[1] / count / NI, st,
+           o[0] - (uint32_t)((count + 1) / 2) * bsum(hash32(8)) - (uint32_t)(count / 2) * bsum(hash32(16)) == want0 ? "ok" : "MISMATCH");
+    return 0;
+}
+
 static int run_check(int mode) {
     uint32_t *d_out, *d_status;
     CK(cudaMalloc(&d_out, 128 * 40 * 4));
@@ -410,6 +499,20 @@ int main(int argc, char **argv) {
     const int mode = argc > 1 ? atoi(argv[1]) : 0;
     const int iters = argc > 2 ? atoi(argv[2]) : 20000;
     if (mode < 10) return run_check(mode);
+    if (mode >= 20) {
+        const int count = argc > 2 ? atoi(argv[2]) : 4096;
+        switch (mode) {
+            case 20: return run_issue<16, 1>(count);
+            case 21: return run_issue<16, 2>(count);
+            case 22: return run_issue<16, 4>(count);
+            case 23: return run_issue<8, 1>(count);
+            case 24: return run_issue<8, 4>(count);
+            case 25: return run_issue<64, 1>(count);
+            case 26: return run_issue<64, 4>(count);
+            case 27: return run_issue<32, 1>(count);
+        }
+        return 1;
+    }
     switch (mode) {
         case 10: return run_pipe<10>(iters);
         case 11: return run_pipe<11>(iters);

@@ -4,15 +4,26 @@
 Workload (BASELINE.json configs[1], SURVEY 8d "C2"): synthetic 1080p 8-bit 60-frame clip
 (I-P-P-P: 15 I + 45 P), 16x16 macroblocks, +/-16 step-1 full search with the reference's own
 cost (wrapped uint8 difference, motion.py:146) and static test (threshold 2000, motion.py:113),
-motion-compensated residual, 8x8 DCT, quantise QF=50 (rint -> int8 indices, lossless at this QF), dequantise, IDCT,
-reconstruction.  One "step" = one pass over one such clip per GPU; `value` = frames of all ranks
-/ max-over-ranks device time with the clip resident in HBM; `e2e` = the same through
-vcs_encode_clip_host with pinned HOST buffers (H2D of the clip and D2H of MVs, costs, flags and indices inside
-the timed region; this leg does not ask for the reconstruction, so its DCT stage runs forward only).  The same numbers for the generalised true-SAD cost ride along in "sad_mode".
+motion-compensated residual, 8x8 DCT, quantise QF=50 (rint -> int8 indices, lossless at this QF).
+One "step" = one pass over one such clip per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-N > 1: launched by torch.distributed.run, one rank per GPU (weak scaling: one clip per rank, no
-data-path collective; NCCL gathers the per-shard motion vectors at the end of every step).
+  value   device-resident: clip in HBM, ME + residual/DCT/quant + dequant/IDCT/reconstruction, outputs left in HBM;
+          frames of all ranks / max-over-ranks device time (CUDA events on the launching stream).
+  e2e     the same clip through vcs_encode_clip_host with pinned HOST buffers: H2D of the clip, ME, residual/DCT/quant,
+          D2H of motion vectors, flags and int8 indices inside the timed region.  Forward half only (what an encoder
+          ships); it is the leg the CPU arm below mirrors.
+  --impl reference / cpu_baseline
+          the CPU port of the reference's algorithm (oracle/, C + SSE2 + OpenMP; the reference itself is pure Python)
+          producing exactly the e2e leg's outputs (mv, cost, flags, int8 indices; forward half only) into buffers
+          allocated once, all host threads.
+  c3_strong (rides along at every N; --workload c3 makes it the headline)
+          BASELINE configs[2]: one 240-frame 2160x3840 clip, +/-32, GOP-sharded over the ranks (strong scaling), NCCL
+          all_gather of the per-shard motion vectors, flags and int8 indices, rank 0 re-encodes a GOP of the last
+          rank's shard and compares it with what it gathered.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3]
+N > 1: launched by torch.distributed.run, one rank per GPU.  C2 is weak scaling (one clip per rank, no data-path
+collective; NCCL gathers the per-shard motion vectors at the end of every step); C3 is strong scaling.
 """
 from __future__ import annotations
 
@@ -129,41 +140,56 @@ def bind_to_gpu_numa_node(index):
     return None
 
 
+def load_synth():
+    """vcs_h264_b200/synth.py (numpy only) loaded by file path: the reference arm never imports the product package."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("vcs_bench_synth", os.path.join(ROOT, "vcs_h264_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_clip(seed):
-    from vcs_h264_b200 import synth
-    return synth.clip(T, H, W, seed=seed)
+    return load_synth().clip(T, H, W, seed=seed)
 
 
 # ------------------------------------------------------------------------------------------------
+CPU_LEG = ("forward half only, like the GPU e2e leg: ME (wrapped cost + static test), MC, residual, 8x8 f64 DCT, rint "
+           "quantiser -> mv, cost, flags, int8 indices into buffers allocated once; C port (oracle/vcs_oracle.c): SSE2 "
+           "costs, OpenMP over macroblocks")
+
+
+def cpu_forward_pass(orc, enc, clip, prm, Q, cores):
+    for p, t in enumerate(t for t in range(T) if t % GOP):
+        enc.encode(p, clip[t], clip[(t // GOP) * GOP], metric=orc.METRIC_WRAP8, static_thr=STATIC_THR, Q=Q,
+                   simd=True, nthreads=cores, **prm)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU port of the reference's algorithm (oracle/vcs_oracle.c; the
     reference itself is pure Python and /root/reference does not exist on the GPU box), all host
-    threads, same config/metric.  Each step = a bounded sample: the first `sample_frames` frames."""
+    threads, same config/metric.  Each step = the whole 60-frame clip."""
     if rank != 0:
         return
     from oracle import oracle as orc
     orc.build()
-    sample_frames = T                                        # the whole clip: 15 I + 45 P at 1080p
-    clip = make_clip(1234)[:sample_frames]
+    clip = make_clip(1234)
     prm = orc.symmetric_search_params(R)
     Q = orc.qtables(QF)
     cores = host_cores()          # explicit: torchrun exports OMP_NUM_THREADS=1
+    enc = orc.ForwardEncoder(H, W, BS, T - T // GOP)
 
-    def step():
-        for t in range(sample_frames):
-            if t % GOP:
-                orc.encode_p(clip[t], clip[(t // GOP) * GOP], BS, metric=orc.METRIC_WRAP8,
-                             static_thr=STATIC_THR, Q=Q, round_mode=1, simd=True, nthreads=cores, **prm)
     for _ in range(args.warmup):
-        step()
+        cpu_forward_pass(orc, enc, clip, prm, Q, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        cpu_forward_pass(orc, enc, clip, prm, Q, cores)
     dt = time.perf_counter() - t0
-    fps = sample_frames * args.steps / dt
-    sample = (f"the whole {sample_frames}-frame clip ({sample_frames // GOP} I + "
-              f"{sample_frames - sample_frames // GOP} P) per step, C port with SSE2 costs + OpenMP over macroblocks")
+    fps = T * args.steps / dt
+    sample = f"the whole {T}-frame clip ({T // GOP} I + {T - T // GOP} P) per step; " + CPU_LEG
+    mapped = sorted({ln.split()[-1] for ln in open("/proc/self/maps") if ln.rstrip().endswith(".so") and ROOT in ln})
     emit({
+        "repo_libraries_mapped": [os.path.relpath(m, ROOT) for m in mapped],   # the CPU port only: never libvcs_b200.so
         "impl": "reference", "metric": METRIC_NAME, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64",
@@ -176,49 +202,83 @@ def run_reference(args, rank, world):
 def workload_config():
     return {"workload": "C2: synthetic 1080p 60-frame clip (15 I + 45 P, I-P-P-P), 16x16 MB, +/-16 step-1 "
                         "full search, reference cost (wrapped u8 diff) + static test thr 2000, residual, "
-                        "8x8 DCT f64, quant QF50 -> int8 indices (lossless: |idx| <= 1024/min(Q) = 102), dequant, IDCT, recon",
+                        "8x8 DCT f64, quant QF50 -> int8 indices (lossless: |idx| <= 1024/min(Q) = 102)",
+            "legs": {"value": "device-resident, forward + dequant, IDCT, reconstruction (outputs stay in HBM)",
+                     "e2e": "pinned host buffers in and out, forward half: mv, flags and the int8 indices in packed form "
+                            "(per-8x8 bitmap + non-zero values, exact) come back",
+                     "cpu": "forward half: mv, cost, flags, int8 indices (what e2e returns), preallocated outputs"},
             "H": H, "W": W, "frames_per_clip": T, "clips_per_step": "one per GPU", "block": BS, "range": R,
             "gop": GOP, "qf": QF, "metric": "wrap8", "static_thr": STATIC_THR,
             "cache": "inputs (373 MB clip) larger than the 126 MB L2; no flush needed",
             "frames_counted": "all T frames (I-frames are stored, as in encoder.py:41-43)"}
 
 
-def cpu_baseline_sample(min_seconds=10.0):
+def cpu_baseline_sample(clip, min_seconds=10.0):
     """The CPU port on the whole 60-frame clip, repeated until >= min_seconds of CPU work."""
     from oracle import oracle as orc
     orc.build()
-    clip = make_clip(1234)
     prm = orc.symmetric_search_params(R)
     Q = orc.qtables(QF)
     cores = host_cores()
+    enc = orc.ForwardEncoder(H, W, BS, T - T // GOP)
     t0 = time.perf_counter()
-    frames = passes = 0
+    passes = 0
     while time.perf_counter() - t0 < min_seconds:
-        for t in range(T):
-            if t % GOP:
-                orc.encode_p(clip[t], clip[(t // GOP) * GOP], BS, metric=orc.METRIC_WRAP8,
-                             static_thr=STATIC_THR, Q=Q, round_mode=1, simd=True, nthreads=cores, **prm)
-            frames += 1
+        cpu_forward_pass(orc, enc, clip, prm, Q, cores)
         passes += 1
     dt = time.perf_counter() - t0
-    return {"value": frames / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{passes} pass(es) over the same 60-frame clip ({frames} frames, I-frames free), "
-                      f"oracle/vcs_oracle.c: SSE2 costs, OpenMP over macroblocks, {dt:.1f} s"}
+    return {"value": T * passes / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{passes} pass(es) over the same 60-frame clip ({T * passes} frames, I-frames free), {dt:.1f} s; " + CPU_LEG}, enc
 
 
-def parity_spot_check(clip, first_p, strip=96):
-    """Outside the timed region: the first P-frame's top `strip` rows against the CPU oracle.
-    MVs / costs / quantised indices / reconstruction are integers: any mismatch is a flip."""
+def parity_check(clip, got, frames=(0, 22, 44)):
+    """Outside the timed region: WHOLE P-frames (every macroblock, index and pixel) of the device-resident run against
+    the CPU oracle, plus the CPU arm's own int8 indices against the GPU's for every P-frame (same outputs, both arms).
+    MVs / costs / flags / quantised indices / reconstruction are integers: any mismatch is a flip."""
     from oracle import oracle as orc
-    o = orc.encode_p(clip[1][:strip + R + BS], clip[0][:strip + R + BS], BS, metric=orc.METRIC_WRAP8,
-                     static_thr=STATIC_THR, Q=orc.qtables(QF), round_mode=1, **orc.symmetric_search_params(R))
-    n = (strip // BS) * (W // BS)
-    return {"rows": strip,
-            "mv_mismatch": int((first_p["mv"].astype(np.int32)[:n] != o["mv"][:n]).any(1).sum()),
-            "cost_mismatch": int((first_p["cost"].view(np.uint32)[:n] != o["cost"][:n]).sum()),
-            "index_flips": int((first_p["coef"][:, :strip].astype(np.float64) != o["planes"][:, :strip]).sum()),
-            "recon_pixel_mismatch": int((first_p["recon"][:strip] != o["recon"][:strip]).sum()),
-            "arithmetic": "float64 DCT with the reference's operation order: flips are 0 by construction"}
+    tot = dict(mv_mismatch=0, cost_mismatch=0, flag_mismatch=0, index_flips=0, recon_pixel_mismatch=0)
+    pidx = [t for t in range(T) if t % GOP]
+    for p in frames:
+        t = pidx[p]
+        o = orc.encode_p(clip[t], clip[(t // GOP) * GOP], BS, metric=orc.METRIC_WRAP8, static_thr=STATIC_THR,
+                         Q=orc.qtables(QF), round_mode=1, simd=True, nthreads=host_cores(), **orc.symmetric_search_params(R))
+        tot["mv_mismatch"] += int((got["mv"][p].astype(np.int32) != o["mv"]).any(1).sum())
+        tot["cost_mismatch"] += int((got["cost"][p].view(np.uint32) != o["cost"]).sum())
+        tot["flag_mismatch"] += int((got["flags"][p] != o["flags"]).sum())
+        tot["index_flips"] += int((got["coef"][p].astype(np.float64) != o["planes"]).sum())
+        tot["recon_pixel_mismatch"] += int((got["recon"][p] != o["recon"]).sum())
+    tot["p_frames_checked_whole"] = [int(p) for p in frames]
+    tot["arithmetic"] = "float64 DCT with the reference's operation order: flips are 0 by construction"
+    return tot
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the two bench kernels from the newest profiles/r*_ncu_full_summary.csv (the committed
+    summary of an `ncu --set full` capture of this command); (None, None, None) when there is none."""
+    import csv
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.csv")),
+                   key=lambda f: int(re.search(r"r(\d+)_", os.path.basename(f)).group(1)))
+    if not files:
+        return None, None, None
+    rows = {r[0]: r for r in csv.reader(open(files[-1])) if r}
+    names, rd, wr = rows.get("Kernel Name"), rows.get("dram__bytes_read.sum"), rows.get("dram__bytes_write.sum")
+    if not (names and rd and wr):
+        return None, None, os.path.basename(files[-1])
+    scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(rd[1], 1e6)
+
+    def pick(pred):
+        for c in range(2, len(names)):
+            if pred(names[c]):
+                try:
+                    return (float(rd[c]) + float(wr[c])) * scale
+                except ValueError:
+                    return None
+        return None
+    me = pick(lambda n: "me_" in n and re.search(r">,\s*0>", n) is not None)
+    dct = pick(lambda n: "dct_stage_kernel<3, 1>" in n)
+    return me, dct, os.path.basename(files[-1])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -293,22 +353,27 @@ def run_b200(args, rank, world, local_rank):
         static_frac = float((dout["flags"] & 1).float().mean().item())
 
         # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------
-        hout = ce.alloc_host_outputs(T, want_coef=True, want_recon=False, pinned=True)
+        # the int8 indices come back PACKED (per-block bitmap + non-zero values, exact); winning costs stay on the device
+        hout = ce.alloc_host_packed(T, want_recon=False, pinned=True)
         for _ in range(max(1, args.warmup)):
-            ce.encode_host(host_in, hout)
+            ce.encode_host_packed(host_in, hout)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ce.encode_host(host_in, hout)
+            ce.encode_host_packed(host_in, hout)
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         if dist is not None:
             dist.barrier()
-        same = bool(torch.equal(hout["mv"], dout["mv"].cpu()) and torch.equal(hout["coef"], dout["coef"].cpu()))
+        from vcs_h264_b200 import container
+        dense = container.expand_packed(hout["bitmap"].numpy(), hout["row_count"].numpy(),
+                                        hout["values"].numpy()[:hout["nvalues"]], H, W)
+        same = bool(torch.equal(hout["mv"], dout["mv"].cpu()) and torch.equal(torch.from_numpy(dense), dout["coef"].cpu()))
+        del dense
         h2d = host_in.numel()
-        d2h = sum(hout[k].numel() * hout[k].element_size() for k in ("mv", "cost", "flags", "coef"))
-        first_p = {k: dout[k][0].cpu().numpy() for k in ("mv", "cost", "coef", "recon")}
-        return dict(first_p=first_p, ms=ms, launches=launches, me_ms=me_ms / max(ncalls, 1), dct_ms=dct_ms / max(ncalls, 1),
+        d2h = sum(hout[k].numel() * hout[k].element_size() for k in ("mv", "flags", "bitmap", "row_count")) + hout["nvalues"]
+        got = {k: dout[k].cpu().numpy() for k in ("mv", "cost", "flags", "coef", "recon")} if metric == _capi.METRIC_WRAP8 and rank == 0 else None
+        return dict(got=got, ms=ms, launches=launches, me_ms=me_ms / max(ncalls, 1), dct_ms=dct_ms / max(ncalls, 1),
                     e2e_fps=world * T * args.steps / dt, e2e_ms=1e3 * dt / args.steps, h2d=h2d, d2h=d2h,
                     clocks=clocks, static_frac=static_frac, host_equals_device=same)
 
@@ -324,6 +389,105 @@ def run_b200(args, rank, world, local_rank):
     wrap = measure(_capi.METRIC_WRAP8)
     sad = measure(_capi.METRIC_SAD) if not args.skip_sad else None
 
+    # ---- BASELINE configs[2] (C3): one 240-frame 4K clip, +/-32, GOP-sharded over the ranks (strong scaling) --------
+    def measure_c3():
+        from vcs_h264_b200 import sharding
+        H3, W3, T3, R3, margin = 2160, 3840, 240, 32, 96
+        steps, warm = args.c3_steps, 1
+        t0, t1 = sharding.frame_range(T3, GOP, rank, world)                  # this rank's GOPs (encoder.py:41-52)
+        base = torch.from_numpy(load_synth().texture(H3, W3, seed=4321, margin=margin)).to(dev)
+        synth = load_synth()
+
+        def frames(ta, tb):
+            """Frames [ta, tb) of THE clip, whichever rank asks: texture panned per frame + integer noise seeded by t."""
+            out = torch.empty((tb - ta, H3, W3, 3), dtype=torch.uint8, device=dev)
+            g = torch.Generator(device=dev)
+            for t in range(ta, tb):
+                dx, dy = synth.pan(t)
+                g.manual_seed(777000 + t)
+                f = base[margin + dy:margin + dy + H3, margin + dx:margin + dx + W3].to(torch.int16)
+                f = f + torch.randint(-2, 3, f.shape, generator=g, device=dev, dtype=torch.int16)
+                out[t - ta] = f.clamp_(0, 255).to(torch.uint8)
+            return out
+        shard = frames(t0, t1)
+        Tl = t1 - t0
+        ce = v.ClipEncoder([H3, W3], block_size=BS, search="full", search_range=R3, gop_len=GOP, qf=QF,
+                           metric=_capi.METRIC_WRAP8, static_thr=STATIC_THR, coef_mode=v.COEF_I8_RINT, device=local_rank)
+        dout = ce.alloc_device_outputs(Tl, want_coef=True, want_recon=False)
+        local = {k: dout[k] for k in ("mv", "flags", "coef")}
+        plan = sharding.GatherPlan(local, T3, GOP, dist) if dist is not None else None
+        gathered = None
+
+        def step():
+            nonlocal gathered
+            ce.encode_device(shard, dout, stream)
+            if plan is not None:
+                gathered = plan.gather(local)            # every rank ends up with the whole clip's vectors and indices
+
+        for _ in range(warm):
+            step()
+        barrier()
+        ce.ctx.enable_kernel_timing(True)
+        l0 = ce.ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        launches = ce.ctx.launch_count() - l0
+        me_ms, dct_ms, ncalls = ce.ctx.kernel_times()
+        ce.ctx.enable_kernel_timing(False)
+        # rank 0 re-encodes one GOP of the LAST rank's shard from the same input and compares with what it gathered
+        check = None
+        if rank == 0:
+            lt0, lt1 = sharding.frame_range(T3, GOP, world - 1, world)
+            gop0 = lt1 - GOP if lt1 - lt0 >= GOP else lt0
+            other = frames(gop0, min(gop0 + GOP, T3))
+            o2 = ce.alloc_device_outputs(other.shape[0], want_coef=True, want_recon=False)
+            ce.encode_device(other, o2, stream)
+            torch.cuda.synchronize()
+            src = gathered if gathered is not None else {k: [local[k]] for k in local}
+            p0 = (gop0 - lt0) // GOP * (GOP - 1)
+            n = o2["mv"].shape[0]
+            check = {"frames": [gop0, gop0 + other.shape[0]], "owner_rank": world - 1,
+                     "mv_equal": bool(torch.equal(src["mv"][-1][p0:p0 + n], o2["mv"])),
+                     "index_equal": bool(torch.equal(src["coef"][-1][p0:p0 + n], o2["coef"])),
+                     "static_fraction": float((o2["flags"] & 1).float().mean().item())}
+            del other, o2
+        # end to end: the shard from pinned host memory, vectors / flags / indices back to pinned host memory
+        host_in3 = torch.empty(shard.shape, dtype=torch.uint8).pin_memory()
+        host_in3.copy_(shard)
+        torch.cuda.synchronize()
+        hout = ce.alloc_host_packed(Tl, want_recon=False, pinned=True)
+        ce.encode_host_packed(host_in3, hout)
+        barrier()
+        tw = time.perf_counter()
+        for _ in range(steps):
+            ce.encode_host_packed(host_in3, hout)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - tw) / steps
+        same = bool(torch.equal(hout["mv"], dout["mv"].cpu()) and hout["nvalues"] == int((dout["coef"] != 0).sum().item()))
+        res = {"workload": "C3: one synthetic 2160x3840 240-frame clip (60 GOPs, I-P-P-P), 16x16 MB, +/-32 step-1 full search, "
+                           "reference cost + static test, residual, 8x8 DCT f64, quant QF50 -> int8 indices; GOP-sharded "
+                           "(sharding.frame_range), per-shard vectors/flags/indices all_gathered over NCCL every step",
+               "frames": T3, "frames_this_rank": Tl, "scaling": "strong", "steps": steps, "warmup": warm,
+               "value": T3 / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+               "me_ms_per_launch_rank0": me_ms / max(ncalls, 1), "dct_ms_per_launch_rank0": dct_ms / max(ncalls, 1),
+               "gpu_launches": launches,
+               "gathered_bytes_per_step_per_rank": plan.bytes_per_step() if plan is not None else 0,
+               "e2e": {"value": T3 / dt, "unit": "frames/s", "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(host_in3.numel()),
+                       "d2h_bytes_per_step": int(sum(hout[k].numel() * hout[k].element_size() for k in ("mv", "flags", "bitmap", "row_count")) + hout["nvalues"]),
+                       "host_equals_device": same},
+               "check": check}
+        del shard, dout, host_in3, hout, base
+        torch.cuda.empty_cache()
+        return res
+
+    c3 = measure_c3() if not args.skip_c3 else None
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -338,8 +502,8 @@ def run_b200(args, rank, world, local_rank):
     pxops = px_ops_per_p_frame(H, W, BS, R) * nP           # per ME launch (one clip)
     peak_pxops = mb["vabsdiff4_acc"]["warp_instr_per_s"] * 32 * 4
 
-    # DRAM bytes per launch from the ncu --set full capture of this command (profiles/r1_ncu_full_summary.csv)
-    ME_TRAFFIC, DCT_TRAFFIC = 381.6e6, 1033.6e6
+    # DRAM bytes per launch from the committed ncu --set full summary of this command (profiles/rN_ncu_full_summary.csv)
+    ME_TRAFFIC, DCT_TRAFFIC, traffic_src = ncu_traffic()
 
     sm_count = ctx0.device_info()["sm_count"]
 
@@ -351,7 +515,7 @@ def run_b200(args, rank, world, local_rank):
         issue_frac = (pxops / 4 / 32 * instr_per_word) / (m["me_ms"] * 1e-3) / issue_peak
         return {"min_instr_per_word": instr_per_word, "frac_of_issue_slots": issue_frac,"bound": "int32", "kernel": "me_tiled_kernel (one launch = 45 P-frames)", "achieved": ach / 1e9,
                 "peak": peak_pxops / 1e9, "unit": "Gpxop/s", "frac": ach / peak_pxops, "traffic": ME_TRAFFIC,
-                "traffic_unit": "bytes of DRAM traffic per launch (ncu); algorithmic input 373.2e6",
+                "traffic_unit": f"bytes of DRAM traffic per launch (ncu, profiles/{traffic_src}); algorithmic input 373.2e6",
                 "ms_per_launch": m["me_ms"],
                 "peak_source": "VABSDIFF4.U8.ACC issue rate measured in this run x 32 lanes x 4 bytes"}
 
@@ -380,8 +544,21 @@ def run_b200(args, rank, world, local_rank):
                             "ms_per_step": sad["ms"] / args.steps, "e2e": sad["e2e_fps"],
                             "roofline": me_roof(sad), "clocks": sad["clocks"]}
     if world == 1 and not args.skip_cpu:
-        line["cpu_baseline"] = cpu_baseline_sample()
-        line["parity_check"] = parity_spot_check(clip_np, wrap["first_p"])
+        line["cpu_baseline"], cpu_enc = cpu_baseline_sample(clip_np)
+        line["parity_check"] = parity_check(clip_np, wrap["got"])
+        line["parity_check"]["cpu_arm_vs_gpu_all_45_p_frames"] = {
+            "mv_mismatch": int((cpu_enc.mv != wrap["got"]["mv"].astype(np.int32)).any(2).sum()),
+            "index_flips": int((cpu_enc.coef != wrap["got"]["coef"]).sum())}
+    if c3 is not None:
+        line["c3_strong"] = c3
+    if args.workload == "c3" and c3 is not None:
+        c2_line = {k: line[k] for k in ("value", "ms_per_step", "e2e", "roofline", "roofline_dct", "config", "scaling") if k in line}
+        line.update({"value": c3["value"], "ms_per_step": c3["ms_per_step"], "scaling": "strong", "steps": c3["steps"],
+                     "warmup": c3["warmup"], "e2e": c3["e2e"], "gpu_launches": c3["gpu_launches"],
+                     "config": {"workload": c3["workload"], "H": 2160, "W": 3840, "frames_per_clip": 240, "block": BS, "range": 32,
+                                "gop": GOP, "qf": QF, "metric": "wrap8", "static_thr": STATIC_THR,
+                                "cache": "inputs (6 GB clip) larger than the 126 MB L2; no flush needed"},
+                     "c2": c2_line})
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -410,6 +587,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-sad", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-c3", action="store_true")
+    ap.add_argument("--c3-steps", type=int, default=2)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c3: the GOP-sharded 4K clip becomes the headline line (strong scaling); c2 rides along as 'c2'")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

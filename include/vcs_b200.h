@@ -178,6 +178,32 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
                          int gop_len, int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags,
                          void *coef, uint8_t *recon);
 
+/*
+ * Packed form of the int8 indices (the wire form of Frame.r, frame.py:1-8; the reference keeps dense float64 planes
+ * and never wrote the zero-run stage its proposal promised).  Per 8x8 block a 64-bit occupancy bitmap (bit 8*i+j =
+ * row i, column j of the block) and, in ONE byte stream for the clip, the block's non-zero values in bit order;
+ * blocks in (P-frame, channel Y/Cr/Cb, block row, block column) order; row_count[p][ch][by] = number of values of a
+ * block row, so rows can be located by a prefix sum.  Exact (lossless) whenever int8 indices are (QF <= 50).
+ *
+ * vcs_encode_clip_host_packed = vcs_encode_clip_host with VCS_COEF_I8_RINT whose coefficients come back packed:
+ * bitmap uint64 [nP][3][H/8][W/8], row_count uint32 [nP][3][H/8], values int8 (values_capacity bytes; 3*H*W*nP is
+ * always enough), *nvalues = bytes written.  The dense planes never cross the bus.
+ */
+int vcs_encode_clip_host_packed(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
+                                int16_t *mv, uint32_t *cost, uint8_t *flags, uint64_t *bitmap, uint32_t *row_count,
+                                int8_t *values, size_t values_capacity, uint64_t *nvalues, uint8_t *recon);
+/* dense int8 planes [nP][3][H][W] -> packed (all DEVICE pointers; *nvalues_host is a host pointer; synchronises) */
+int vcs_pack_coef_dev(vcs_ctx *ctx, int H, int W, int nP, const int8_t *coef, uint64_t *bitmap, uint32_t *row_count,
+                      int8_t *values, uint64_t *nvalues_host);
+/* the exact inverse (all DEVICE pointers, enqueued on the context's stream); a stream shorter than its bitmaps claim
+ * is never read past its end: the affected blocks decode to zero and the context reports VCS_E_INVALID */
+int vcs_unpack_coef_dev(vcs_ctx *ctx, int H, int W, int nP, const uint64_t *bitmap, const uint32_t *row_count,
+                        const int8_t *values, uint64_t nvalues, int8_t *coef);
+/* vcs_decode_clip_host from the packed form (host buffers) */
+int vcs_decode_clip_host_packed(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_frames, int T, int gop_len,
+                                const int16_t *mv, const uint64_t *bitmap, const uint32_t *row_count,
+                                const int8_t *values, uint64_t nvalues, uint8_t *recon);
+
 /* ---- decoder side: Decoder._reconstruct_P_frame over a clip (decoder.py:52-69) --------------------- */
 /* ref_frames: the ORIGINAL I-frames only, uint8 [nG][H][W][3] (Decoder.ref_frames); mv / coef indexed by
  * P-frame ordinal as the encoder wrote them; recon: uint8 [nP][H][W][3] = MC(ref, mv) + decompress(coef). */

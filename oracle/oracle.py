@@ -218,6 +218,32 @@ def encode_p(cur, ref, bs, lo, hi, step, slack, metric=METRIC_WRAP8, static_thr=
     return dict(mv=mv, cost=cost, flags=flags, planes=planes, recon=recon)
 
 
+class ForwardEncoder:
+    """bench.py's CPU arm: Encoder._process_P_frame (encoder.py:49-70) with the rounded quantiser, forward half
+    only, int8 indices -- the same outputs as the GPU end-to-end leg -- into buffers allocated ONCE here."""
+
+    def __init__(self, H, W, bs, nP):
+        N = (H // bs) * (W // bs)
+        self.H, self.W, self.bs = H, W, bs
+        self.mv = np.zeros((nP, N, 2), np.int32)
+        self.cost = np.zeros((nP, N), np.uint32)
+        self.flags = np.zeros((nP, N), np.uint8)
+        self.coef = np.zeros((nP, 3, H, W), np.int8)
+        self.scratch = np.zeros(2 * H * W * 3, np.uint8)
+
+    def encode(self, p, cur, ref, lo, hi, step, slack, metric=METRIC_WRAP8, static_thr=2000, Q=None, simd=True,
+               nthreads=0):
+        cur, ref = _u8(cur), _u8(ref)
+        Q = qtables(50.0) if Q is None else Q
+        rc = lib().vcs_oracle_encode_p_i8(_p(cur, C.c_uint8), _p(ref, C.c_uint8), self.H, self.W, self.bs, lo, hi,
+                                          step, slack, metric, C.c_longlong(static_thr), _p(Q, C.c_double),
+                                          int(simd), nthreads, _p(self.mv[p], C.c_int32), _p(self.cost[p], C.c_uint32),
+                                          _p(self.flags[p], C.c_uint8), _p(self.coef[p], C.c_int8),
+                                          _p(self.scratch, C.c_uint8))
+        if rc:
+            raise ValueError(f"vcs_oracle_encode_p_i8 rc={rc}")
+
+
 def max_threads():
     return lib().vcs_oracle_max_threads()
 

@@ -350,8 +350,18 @@ void vcs_oracle_idct2(const double *X, double *P) {
  * round_mode 1 = DCTCompression/dct.py:179  np.round(np.divide(d, Q)) (half-to-even).
  * planes: 3 x H x W float64, same geometry as the image.
  */
+static int compress_impl(const uint8_t *bgr, int H, int W, const double *Q, int round_mode,
+                         int nthreads, double *planes, int8_t *idx8);
+
 int vcs_oracle_compress(const uint8_t *bgr, int H, int W, const double *Q, int round_mode,
                         int nthreads, double *planes) {
+    return compress_impl(bgr, H, W, Q, round_mode, nthreads, planes, NULL);
+}
+
+/* idx8 != NULL: the rounded indices are stored as int8 instead of float64 (the compact form the CUDA path
+ * ships at QF <= 50, where |index| <= 1024 / min(Q) <= 127); same arithmetic, narrower store. */
+static int compress_impl(const uint8_t *bgr, int H, int W, const double *Q, int round_mode,
+                         int nthreads, double *planes, int8_t *idx8) {
     if (H % 8 || W % 8) return -1;
     double C[64], Ct[64];
     vcs_oracle_dct_matrix(C);
@@ -378,7 +388,8 @@ int vcs_oracle_compress(const uint8_t *bgr, int H, int W, const double *Q, int r
             for (int u = 0; u < 8; ++u) {
                 double q = D[v * 8 + u] / Q[ch * 64 + v * 8 + u];
                 if (round_mode) q = nearbyint(q);
-                planes[(size_t)ch * npix + (size_t)(by + v) * W + bx + u] = q;
+                if (idx8) idx8[(size_t)ch * npix + (size_t)(by + v) * W + bx + u] = (int8_t)q;
+                else planes[(size_t)ch * npix + (size_t)(by + v) * W + bx + u] = q;
             }
     }
     free(ycc);
@@ -466,6 +477,27 @@ done:
     if (!planes) free(planes_l);
     free(pred); free(resid); free(dec);
     return rc;
+}
+
+/*
+ * The forward half only (encoder.py:49-70), indices as int8: ME, MC, residual, DCT, rounded quantiser.  This is
+ * exactly what bench.py's end-to-end GPU leg returns (mv, cost, flags, int8 indices), so it is the unit its CPU
+ * arm times.  scratch: caller-provided 2 * H*W*3 bytes (pred, resid) so that nothing is allocated per frame.
+ */
+int vcs_oracle_encode_p_i8(const uint8_t *cur, const uint8_t *ref, int H, int W, int bs, int lo,
+                           int hi, int step, int slack, int metric, long long static_thr,
+                           const double *Q, int use_simd, int nthreads,
+                           int32_t *mv, uint32_t *cost, uint8_t *flags, int8_t *idx8, uint8_t *scratch) {
+    const size_t n = (size_t)H * W * 3;
+    if (!mv || !cost || !flags || !idx8 || !scratch) return -1;
+    uint8_t *pred = scratch, *resid = scratch + n;
+    int rc = vcs_oracle_me(cur, ref, H, W, bs, lo, hi, step, slack, metric, static_thr, use_simd,
+                           nthreads, mv, cost, flags);
+    if (rc) return rc;
+    rc = vcs_oracle_mc(ref, H, W, bs, mv, pred);
+    if (rc) return rc;
+    vcs_oracle_residual(cur, pred, n, resid);
+    return compress_impl(resid, H, W, Q, 1, nthreads, NULL, idx8);
 }
 
 int vcs_oracle_max_threads(void) {

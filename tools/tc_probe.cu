@@ -40,6 +40,17 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int ma
     }
     return false;
 }
+// non-suspending poll (mbarrier.test_wait): separates the barrier's own latency from try_wait's sleep/wake-up
+__device__ __forceinline__ bool mbar_poll(uint64_t *bar, uint32_t parity, int max_tries = 1 << 22) {
+    for (int t = 0; t < max_tries; ++t) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -429,6 +440,144 @@ static int run_issue(int count) {
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// part 4 (mode 16..19): the protocol the search kernel would use.  No dedicated MMA warp: the 4 warps of a lane-quarter
+// group meet at a named barrier once their stores are visible, and ONE of them (rotating) issues the group's MMAs and
+// the commit that frees the A buffer; the others only arrive and go on.  ROWS window rows per step, NBUF A buffers.
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int ROWS, int NBUF, bool DEFER, bool POLL>
+__global__ void __launch_bounds__(512, 1) k_pipe2(int iters, uint32_t seed, uint32_t *out, long long *cyc, uint32_t *status) {
+    __shared__ __align__(128) uint8_t sB[2][512];
+    __shared__ __align__(8) uint64_t empty[4][4];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 2 * 512; i += blockDim.x) (&sB[0][0])[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < 2 * 32; i += blockDim.x) { const int q = i / 32, k = i % 32; sB[q][k * 16 + 8 * q + k / 4] = 1; }
+    if (tid == 0) {
+        for (int g = 0; g < 4; ++g)
+            for (int b = 0; b < 4; ++b) mbar_init(&empty[g][b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tc_alloc(&tmem_slot, 512);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    const int g = warp >> 2, quarter = warp & 3;
+    const uint32_t gcol = tbase + 128u * g;                    // D at +0 (16 columns), A buffers at +64 + 16*ROWS*b
+    const uint32_t lane_base = gcol + ((uint32_t)(32 * quarter) << 16);
+    const uint32_t idesc = make_idesc(128, 16, 1);
+    const uint64_t d0 = make_desc(smem_u32(&sB[0][0]), 128, 128), d1 = make_desc(smem_u32(&sB[1][0]), 128, 128);
+    bool ok = true;
+    uint32_t c[16], ch[16], z[16 * ROWS];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { c[j] = hash32(seed + tid * 16 + j) & 0x7f7f7f7fu; ch[j] = hash32(seed * 3 + tid * 16 + j) & 0x80808080u; }
+    uint32_t r = hash32(seed + tid);
+    {
+        uint32_t zeros[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) zeros[j] = 0;
+        tc_st16(lane_base, zeros);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    auto publish = [&](int it) {      // stores of step `it` are done: meet the group; the step's issuer feeds the tensor core
+        const int b = it % NBUF;
+        tc_wait_st();
+        tc_fence_before();
+        const int id = 1 + NBUF * g + b;
+        if (quarter == (it & 3)) {
+            bar_sync(id, 128);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a = gcol + 64 + 16 * ROWS * b;
+#pragma unroll
+                for (int rr = 0; rr < ROWS; ++rr) {
+                    tc_mma_i8_ts(gcol, a + 16 * rr, d0, idesc, 1);
+                    tc_mma_i8_ts(gcol, a + 16 * rr + 8, d1, idesc, 1);
+                }
+                tc_commit(&empty[g][b]);
+            }
+            __syncwarp();
+        } else {
+            bar_arrive(id, 128);
+        }
+    };
+    long long waited = 0, published = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        const int b = it % NBUF;
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) {
+            r = r * 1664525u + 1013904223u;
+            uint32_t r1, r2;
+            asm volatile("lop3.b32 %0, %1, %2, %2, 0xfc;" : "=r"(r1) : "r"(r), "r"(0x80808080u));
+            r2 = r1 - r;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(z[16 * rr + j]) : "r"(r1 - c[j]), "r"(r2), "r"(ch[j]));
+        }
+        if (DEFER && it > 0) publish(it - 1);
+        if (it >= NBUF) {
+            const long long w0 = clock64();
+            ok = ok && (POLL ? mbar_poll(&empty[g][b], (uint32_t)(it / NBUF - 1) & 1) : mbar_wait(&empty[g][b], (uint32_t)(it / NBUF - 1) & 1));
+            waited += clock64() - w0;
+        }
+        tc_fence_after();
+#pragma unroll
+        for (int rr = 0; rr < ROWS; ++rr) tc_st16(lane_base + 64 + 16 * ROWS * b + 16 * rr, z + 16 * rr);
+        if (!DEFER) { const long long w0 = clock64(); publish(it); published += clock64() - w0; }
+    }
+    if (DEFER) publish(iters - 1);
+    const long long t1 = clock64();
+    if (tid == 0) { cyc[blockIdx.x] = t1 - t0; if (blockIdx.x == 0) { cyc[gridDim.x] = waited; cyc[gridDim.x + 1] = published; } }
+    // drain: the last NBUF commits
+    for (int k = 0; k < NBUF && k < iters; ++k) {
+        const int it = iters - 1 - k;
+        ok = ok && mbar_wait(&empty[g][it % NBUF], (uint32_t)(it / NBUF) & 1);
+    }
+    if (!ok) atomicAdd(status, 1);
+    tc_fence_after();
+    uint32_t d[16];
+    tc_ld16(lane_base, d);
+    tc_wait_ld();
+    uint32_t sum = r;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sum += d[j];
+    out[blockIdx.x * blockDim.x + tid] = sum;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc_dealloc(tbase, 512);
+}
+
+template <int ROWS, int NBUF, bool DEFER, bool POLL>
+static int run_pipe2(int iters, int mode) {
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    uint32_t *d_out, *d_status; long long *d_cyc;
+    CK(cudaMalloc(&d_out, (size_t)sms * 512 * 4)); CK(cudaMalloc(&d_cyc, (sms + 2) * 8)); CK(cudaMalloc(&d_status, 4));
+    CK(cudaMemset(d_status, 0, 4));
+    k_pipe2<ROWS, NBUF, DEFER, POLL><<<sms, 512>>>(iters / 8 + 1, 1234u, d_out, d_cyc, d_status);
+    k_pipe2<ROWS, NBUF, DEFER, POLL><<<sms, 512>>>(iters, 1234u, d_out, d_cyc, d_status);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    long long cyc, extra[2]; uint32_t st;
+    CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(extra, d_cyc + sms, 16, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&st, d_status, 4, cudaMemcpyDeviceToHost));
+    printf("pipe2 mode %d (rows/step %d, buffers %d, deferred publish %d, poll %d): %lld clk for %d steps -> %.3f clk/word/SMSP; warp 0 per step: %.0f clk waiting for a free buffer, %.0f clk in publish; timeouts %u\n",
+           mode, ROWS, NBUF, (int)DEFER, (int)POLL, cyc, iters, (double)cyc / (4.0 * iters * ROWS * 16), (double)extra[0] / iters, (double)extra[1] / iters, st);
+    return 0;
+}
+
 static int run_check(int mode) {
     uint32_t *d_out, *d_status;
     CK(cudaMalloc(&d_out, 128 * 40 * 4));
@@ -499,7 +648,7 @@ int main(int argc, char **argv) {
     const int mode = argc > 1 ? atoi(argv[1]) : 0;
     const int iters = argc > 2 ? atoi(argv[2]) : 20000;
     if (mode < 10) return run_check(mode);
-    if (mode >= 20) {
+    if (mode >= 20 && mode < 30) {
         const int count = argc > 2 ? atoi(argv[2]) : 4096;
         switch (mode) {
             case 20: return run_issue<16, 1>(count);
@@ -514,6 +663,12 @@ int main(int argc, char **argv) {
         return 1;
     }
     switch (mode) {
+        case 16: return run_pipe2<1, 3, false, false>(iters, mode);
+        case 17: return run_pipe2<2, 2, false, false>(iters, mode);
+        case 18: return run_pipe2<1, 3, true, false>(iters, mode);
+        case 19: return run_pipe2<2, 2, true, false>(iters, mode);
+        case 36: return run_pipe2<1, 3, false, true>(iters, mode);
+        case 37: return run_pipe2<2, 2, false, true>(iters, mode);
         case 10: return run_pipe<10>(iters);
         case 11: return run_pipe<11>(iters);
         case 12: return run_pipe<12>(iters);

@@ -12,6 +12,13 @@ what crosses NCCL and what a file would hold:
     mv      int16[n_p][n_blocks][2]  ([dx, dy], raster order: MotionProcessor.process_motion_prediction)
     coef    [n_p][3][H][W] in the clip's coefficient format (float64 like DCTCompressor.compress, int16 or int8 indices)
 
+Version 2 stores the int8 indices PACKED (include/vcs_b200.h, vcs_encode_clip_host_packed): instead of `coef` it holds
+    bitmap    uint64[n_p][3][H/8][W/8]   occupancy of every 8x8 block (bit 8*i+j = row i, column j)
+    row_count uint32[n_p][3][H/8]        values per block row
+    values    int8[nvalues]              the non-zero indices in block / bit order
+and the header's reserved field carries nvalues.  `expand_packed()` / `compact_dense()` convert between the two forms on
+the host (byte shuffling only, for marshalling into the reference's Frame objects; the decoder's arithmetic stays on the GPU).
+
 `to_frames()` rebuilds the reference's own objects (Frame lists, block coords, ref_frames) from a container, so the
 reference's Decoder -- or this package's drop-in Decoder -- can consume it unchanged.  No entropy stage: with the
 reference's wrapped residual the indices are dense (43 % non-zero at QF 50 on the bench clip).
@@ -27,7 +34,7 @@ from .frame import Frame
 
 MAGIC = b"VCSB200\0"
 VERSION = 1
-_HDR = struct.Struct("<8s9Id12x")
+_HDR = struct.Struct("<8s9IdQ4x")
 COEF_DTYPES = {_capi.COEF_F64: np.float64, _capi.COEF_F64_RINT: np.float64,
                _capi.COEF_I16_RINT: np.int16, _capi.COEF_I8_RINT: np.int8}
 
@@ -43,8 +50,52 @@ def pack(i_frames, mv, coef, *, T, block_size, gop_len, coef_mode, qf=50.0, Q=No
     if n_i != (T + gop_len - 1) // gop_len or mv.shape != (n_p, N, 2) or coef.shape != (n_p, 3, H, W):
         raise ValueError("array shapes do not match T / gop_len / block_size")
     Q = np.ascontiguousarray(_capi.q_tables(qf) if Q is None else Q, np.float64).reshape(3, 8, 8)
-    hdr = _HDR.pack(MAGIC, VERSION, T, H, W, block_size, gop_len, coef_mode, n_p, N, float(qf))
+    hdr = _HDR.pack(MAGIC, VERSION, T, H, W, block_size, gop_len, coef_mode, n_p, N, float(qf), 0)
     return b"".join([hdr, Q.tobytes(), i_frames.tobytes(), mv.tobytes(), coef.tobytes()])
+
+
+def pack_packed(i_frames, mv, bitmap, row_count, values, nvalues=None, *, T, block_size, gop_len, qf=50.0, Q=None) -> bytes:
+    """Version-2 container: int8 indices in packed form (bitmap uint64 [n_p,3,H/8,W/8], row_count uint32 [n_p,3,H/8],
+    values int8 [>= nvalues])."""
+    i_frames = np.ascontiguousarray(i_frames, np.uint8)
+    n_i, H, W, _ = i_frames.shape
+    n_p = _capi.num_p_frames(T, gop_len)
+    N = (H // block_size) * (W // block_size)
+    mv = np.ascontiguousarray(mv, np.int16)
+    bitmap = np.ascontiguousarray(np.asarray(bitmap)).view(np.uint64)
+    row_count = np.ascontiguousarray(np.asarray(row_count)).view(np.uint32)
+    nvalues = int(row_count.sum()) if nvalues is None else int(nvalues)
+    values = np.ascontiguousarray(np.asarray(values).reshape(-1)[:nvalues], np.int8)
+    if (n_i != (T + gop_len - 1) // gop_len or mv.shape != (n_p, N, 2) or bitmap.shape != (n_p, 3, H // 8, W // 8)
+            or row_count.shape != (n_p, 3, H // 8) or values.size != nvalues or int(row_count.sum()) != nvalues):
+        raise ValueError("array shapes do not match T / gop_len / block_size / nvalues")
+    Q = np.ascontiguousarray(_capi.q_tables(qf) if Q is None else Q, np.float64).reshape(3, 8, 8)
+    hdr = _HDR.pack(MAGIC, 2, T, H, W, block_size, gop_len, _capi.COEF_I8_RINT, n_p, N, float(qf), nvalues)
+    return b"".join([hdr, Q.tobytes(), i_frames.tobytes(), mv.tobytes(), bitmap.tobytes(), row_count.tobytes(), values.tobytes()])
+
+
+def expand_packed(bitmap, row_count, values, H, W):
+    """Packed indices -> dense int8 [n_p,3,H,W] (host-side byte shuffling; the GPU twin is vcs_unpack_coef_dev)."""
+    bitmap = np.ascontiguousarray(np.asarray(bitmap)).view(np.uint64)
+    n_p = bitmap.shape[0]
+    bits = np.unpackbits(bitmap.view(np.uint8).reshape(n_p, 3, H // 8, W // 8, 8), axis=-1, bitorder="little").astype(bool)
+    bits = bits.reshape(n_p, 3, H // 8, W // 8, 8, 8)      # [.., block row, block column, row in block, column in block]
+    values = np.asarray(values, np.int8).reshape(-1)
+    if int(bits.sum()) != values.size or int(np.asarray(row_count).view(np.uint32).sum()) != values.size:
+        raise ValueError("bitmaps, row counts and value stream disagree")
+    blocks = np.zeros(bits.shape, np.int8)                 # [n_p,3,H/8,W/8,8,8]
+    blocks[bits] = values
+    return np.ascontiguousarray(blocks.transpose(0, 1, 2, 4, 3, 5)).reshape(n_p, 3, H, W)
+
+
+def compact_dense(coef):
+    """Dense int8 [n_p,3,H,W] -> (bitmap uint64, row_count uint32, values int8): the inverse of expand_packed."""
+    coef = np.ascontiguousarray(coef, np.int8)
+    n_p, _, H, W = coef.shape
+    blocks = coef.reshape(n_p, 3, H // 8, 8, W // 8, 8).transpose(0, 1, 2, 4, 3, 5)
+    nz = blocks != 0
+    bitmap = np.packbits(nz.reshape(n_p, 3, H // 8, W // 8, 64), axis=-1, bitorder="little").view(np.uint64)[..., 0]
+    return (np.ascontiguousarray(bitmap), nz.sum(axis=(3, 4, 5)).astype(np.uint32), np.ascontiguousarray(blocks[nz]))
 
 
 def check_mv_range(mv, H, W, bs):
@@ -63,14 +114,19 @@ def unpack(buf) -> dict:
     buf = memoryview(buf)
     if len(buf) < _HDR.size:
         raise ValueError("truncated container")
-    magic, ver, T, H, W, bs, gop, cm, n_p, N, qf = _HDR.unpack(buf[:_HDR.size])
-    if magic != MAGIC or ver != VERSION:
+    magic, ver, T, H, W, bs, gop, cm, n_p, N, qf, nvalues = _HDR.unpack(buf[:_HDR.size])
+    if magic != MAGIC or ver not in (VERSION, 2):
         raise ValueError("not a vcs_b200 container (magic / version)")
     if cm not in COEF_DTYPES or gop < 2 or bs < 1 or n_p != _capi.num_p_frames(T, gop) or N != (H // bs) * (W // bs):
         raise ValueError("inconsistent container header")
     n_i = (T + gop - 1) // gop
     dt = np.dtype(COEF_DTYPES[cm])
-    sizes = [3 * 64 * 8, n_i * H * W * 3, n_p * N * 2 * 2, n_p * 3 * H * W * dt.itemsize]
+    if ver == 2:
+        if cm != _capi.COEF_I8_RINT or H % 8 or W % 8:
+            raise ValueError("inconsistent container header")
+        sizes = [3 * 64 * 8, n_i * H * W * 3, n_p * N * 2 * 2, n_p * 3 * (H // 8) * (W // 8) * 8, n_p * 3 * (H // 8) * 4, nvalues]
+    else:
+        sizes = [3 * 64 * 8, n_i * H * W * 3, n_p * N * 2 * 2, n_p * 3 * H * W * dt.itemsize]
     if len(buf) != _HDR.size + sum(sizes):
         raise ValueError("container size does not match its header")
     off, parts = _HDR.size, []
@@ -79,6 +135,16 @@ def unpack(buf) -> dict:
         off += n
     mv = np.frombuffer(parts[2], np.int16).reshape(n_p, N, 2)
     check_mv_range(mv, H, W, bs)
+    if ver == 2:
+        bitmap = np.frombuffer(parts[3], np.uint64).reshape(n_p, 3, H // 8, W // 8)
+        row_count = np.frombuffer(parts[4], np.uint32).reshape(n_p, 3, H // 8)
+        values = np.frombuffer(parts[5], np.int8)
+        if int(row_count.sum()) != nvalues:
+            raise ValueError("row counts do not add up to the value stream length")
+        return dict(T=T, H=H, W=W, block_size=bs, gop_len=gop, coef_mode=cm, qf=qf, version=2,
+                    Q=np.frombuffer(parts[0], np.float64).reshape(3, 8, 8),
+                    i_frames=np.frombuffer(parts[1], np.uint8).reshape(n_i, H, W, 3), mv=mv,
+                    bitmap=bitmap, row_count=row_count, values=values, nvalues=nvalues)
     return dict(T=T, H=H, W=W, block_size=bs, gop_len=gop, coef_mode=cm, qf=qf,
                 Q=np.frombuffer(parts[0], np.float64).reshape(3, 8, 8),
                 i_frames=np.frombuffer(parts[1], np.uint8).reshape(n_i, H, W, 3),
@@ -91,6 +157,8 @@ def to_frames(c: dict):
     Frame("I", None, None, None, t, ref_idx) with the image in ref_frames; P-frames carry mv as [dx,dy] int lists,
     r as three float64 planes (the rounded indices as floats when the clip holds indices) and c as [x,y] coords."""
     H, W, bs, g = c["H"], c["W"], c["block_size"], c["gop_len"]
+    if "coef" not in c:                                   # version 2: packed indices
+        c = dict(c, coef=expand_packed(c["bitmap"], c["row_count"], c["values"], H, W))
     coords = [[x, y] for y in range(0, H - bs + 1, bs) for x in range(0, W - bs + 1, bs)]
     frames, refs, p = [], [], 0
     for t in range(c["T"]):

@@ -71,6 +71,13 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
     return ((unsigned long long)hi << 32) | lo;
 }
 
+__device__ __forceinline__ unsigned long long shfl_up_u64(unsigned long long v, int d) {
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    lo = __shfl_up_sync(0xffffffffu, lo, d);
+    hi = __shfl_up_sync(0xffffffffu, hi, d);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {

@@ -20,13 +20,15 @@
 #include "me_generic.cuh"
 #include "me_tiled.cuh"
 #include "microbench.cuh"
+#include "pack.cuh"
 
 using namespace vcs;
 
 namespace {
 
-constexpr int NUM_DEV_SLOTS = 12;
-enum DevSlot { S_FRAMES = 0, S_MV, S_COST, S_FLAGS, S_COEF, S_RECON, S_AUX0, S_AUX1, S_AUX2, S_MB, S_CYC };
+constexpr int NUM_DEV_SLOTS = 17;
+enum DevSlot { S_FRAMES = 0, S_MV, S_COST, S_FLAGS, S_COEF, S_RECON, S_AUX0, S_AUX1, S_AUX2, S_MB, S_CYC,
+               S_PK_BITMAP, S_PK_ROWCNT, S_PK_ROWOFF, S_PK_VALUES, S_PK_TOTAL };
 
 struct EvTriple {
     cudaEvent_t e0, e1, e2;
@@ -54,6 +56,9 @@ struct vcs_ctx {
     size_t ev_used = 0;
     MeTiledState tiled;
     int *h_errflag = nullptr;          // pinned, mapped: kernels store 1 when a motion vector leaves the frame
+    unsigned long long *h_segend = nullptr;   // pinned: running value-stream length after each pipeline segment
+    size_t h_segend_cap = 0;
+    std::vector<cudaEvent_t> seg_events;
     uint64_t q_version = 0;
 };
 
@@ -278,6 +283,37 @@ int encode_dev(vcs_ctx *ctx, cudaStream_t st, const vcs_me_params *p, const Fram
     return VCS_OK;
 }
 
+// ---- packed coefficient stream (pack.cuh) ----------------------------------------------------------------
+struct PackedHost {              // host destinations of vcs_encode_clip_host_packed
+    unsigned long long *bitmap;  // [nP][3][H/8][W/8]
+    uint32_t *row_count;         // [nP][3][H/8]
+    int8_t *values;              // value stream, capacity bytes
+    size_t capacity;
+    unsigned long long *nvalues; // out: length of the stream
+};
+
+static int pack_grid(vcs_ctx *ctx, int nrows) {
+    long long g = ((long long)nrows + PACK_WARPS - 1) / PACK_WARPS;
+    const long long cap = (long long)ctx->sm_count * 8;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// dense int8 planes of nP frames -> bitmaps, row counts, row offsets and values on the device.  *d_total (device,
+// 8 bytes) is the running stream length: the rows of this call are appended after it.  d_segend (device or mapped,
+// may be null) receives the new total.
+static int launch_pack(vcs_ctx *ctx, cudaStream_t st, int H, int W, int nP, const int8_t *coef,
+                       unsigned long long *d_bitmap, uint32_t *d_rowcnt, unsigned long long *d_rowoff,
+                       int8_t *d_values, unsigned long long *d_total, unsigned long long *d_segend) {
+    const int nrows = nP * 3 * (H / 8);
+    if (nrows <= 0) return VCS_OK;
+    pack_count_kernel<<<pack_grid(ctx, nrows), 32 * PACK_WARPS, 0, st>>>(coef, W, nrows, d_bitmap, d_rowcnt);
+    pack_scan_kernel<<<1, 1024, 0, st>>>(d_rowcnt, nrows, d_rowoff, d_total, d_segend);
+    pack_write_kernel<<<pack_grid(ctx, nrows), 32 * PACK_WARPS, 0, st>>>(coef, W, nrows, d_rowoff, d_values);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    return VCS_OK;
+}
+
 }  // namespace
 
 template <int W>
@@ -432,6 +468,8 @@ int vcs_destroy(vcs_ctx *ctx) {
     if (ctx->h_errflag) cudaFreeHost(ctx->h_errflag);
     for (auto &t : ctx->ev_pool) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
     for (auto &e : ctx->chunk_events) cudaEventDestroy(e);
+    for (auto &e : ctx->seg_events) cudaEventDestroy(e);
+    if (ctx->h_segend) cudaFreeHost(ctx->h_segend);
     me_tiled_destroy(ctx->tiled);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
@@ -761,9 +799,9 @@ int vcs_encode_clip_dev(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fra
                       vcs_num_p_frames(T, gop_len), coef_mode, mv, cost, flags, coef, recon);
 }
 
-int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
-                         int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef,
-                         uint8_t *recon) {
+static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
+                                 int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef,
+                                 uint8_t *recon, const PackedHost *pk) {
     VCS_ENTER(ctx);
     int rc = check_me_params(ctx, p);
     if (rc) return rc;
@@ -779,8 +817,18 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
     if ((rc = dev_buf(ctx, S_MV, (size_t)nP * N * 4 + 4, (void **)&d_mv))) return rc;
     if ((rc = dev_buf(ctx, S_COST, (size_t)nP * N * 4 + 4, (void **)&d_cost))) return rc;
     if ((rc = dev_buf(ctx, S_FLAGS, (size_t)nP * N + 4, (void **)&d_fl))) return rc;
-    if (coef && (rc = dev_buf(ctx, S_COEF, (size_t)nP * npix * 3 * ce + 8, &d_coef))) return rc;
+    if ((coef || pk) && (rc = dev_buf(ctx, S_COEF, (size_t)nP * npix * 3 * ce + 8, &d_coef))) return rc;
     if (recon && (rc = dev_buf(ctx, S_RECON, (size_t)nP * fs + 4, (void **)&d_rec))) return rc;
+    // packed sink: the dense int8 planes stay on the device, bitmaps + row counts + the value stream travel
+    const int rows_per_p = 3 * (p->H / 8), nbx8 = p->W / 8;
+    unsigned long long *d_bitmap = nullptr, *d_rowoff = nullptr, *d_total = nullptr;
+    uint32_t *d_rowcnt = nullptr; int8_t *d_values = nullptr;
+    if (pk) {
+        if ((rc = dev_buf(ctx, S_PK_BITMAP, (size_t)nP * rows_per_p * nbx8 * 8 + 8, (void **)&d_bitmap))) return rc;
+        if ((rc = dev_buf(ctx, S_PK_ROWCNT, (size_t)nP * rows_per_p * 4 + 4, (void **)&d_rowcnt))) return rc;
+        if ((rc = dev_buf(ctx, S_PK_ROWOFF, (size_t)nP * rows_per_p * 8 + 8, (void **)&d_rowoff))) return rc;
+        if ((rc = dev_buf(ctx, S_PK_VALUES, (size_t)nP * npix * 3 + 64, (void **)&d_values))) return rc;
+    }
 
     // Pipeline: copy-in on s_h2d, kernels on the compute stream, copy-out on s_d2h, chained with events; PCIe
     // is full duplex so the three overlap.  Segments are ranges of P-frames (they may start and end inside a GOP):
@@ -832,6 +880,24 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
         }
     }
     const int nsegs = (int)sizes.size();
+    if (pk) {
+        if ((size_t)nsegs > ctx->h_segend_cap) {
+            if (ctx->h_segend) cudaFreeHost(ctx->h_segend);
+            ctx->h_segend = nullptr; ctx->h_segend_cap = 0;
+            CK(ctx, cudaHostAlloc((void **)&ctx->h_segend, sizeof(unsigned long long) * (size_t)nsegs, cudaHostAllocDefault));
+            ctx->h_segend_cap = (size_t)nsegs;
+        }
+        while ((int)ctx->seg_events.size() < nsegs) {
+            cudaEvent_t e;
+            CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->seg_events.push_back(e);
+        }
+        // [0]: running stream length; [1 + c]: its value after segment c (a private slot per segment: the download
+        // stream may read it while the compute stream is already extending the stream for the next segment)
+        if ((rc = dev_buf(ctx, S_PK_TOTAL, 8 * (size_t)(nsegs + 1), (void **)&d_total))) return rc;
+        CK(ctx, cudaMemsetAsync(d_total, 0, 8, ctx->stream));
+        *pk->nvalues = 0;
+    }
     while ((int)ctx->chunk_events.size() < 2 * nsegs) {
         cudaEvent_t e;
         CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -840,6 +906,21 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
     // (Running consecutive searches on two streams so that one fills the other's tail was tried and is slower:
     // the persistent search CTAs of the next chunk then keep the DCT stage of this chunk off the SMs.)
     cudaStream_t sc = ctx->stream;
+    unsigned long long host_values = 0;      // bytes of the value stream already queued for download
+    int seg_done = 0;                        // segments whose values have been queued
+    auto drain_values = [&](int upto) -> int {   // queue the value downloads of segments [seg_done, upto)
+        for (; seg_done < upto; ++seg_done) {
+            CK(ctx, cudaEventSynchronize(ctx->seg_events[seg_done]));     // its stream length has landed
+            const unsigned long long end = ctx->h_segend[seg_done];
+            if (end > pk->capacity) return fail(ctx, VCS_E_INVALID, "value buffer too small (%llu > %zu bytes)", end, pk->capacity);
+            if (end > host_values)
+                CK(ctx, cudaMemcpyAsync(pk->values + host_values, d_values + host_values, end - host_values,
+                                        cudaMemcpyDeviceToHost, ctx->s_d2h));
+            host_values = end;
+        }
+        *pk->nvalues = host_values;
+        return VCS_OK;
+    };
     auto pipeline = [&]() -> int {
     int uploaded = 0, p0 = 0;
     for (int c = 0; c < nsegs; ++c) {                    // frames after the last P-frame are never needed on the device
@@ -862,9 +943,24 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
                             d_coef ? (void *)((char *)d_coef + (size_t)p0 * npix * 3 * ce) : nullptr,
                             d_rec ? d_rec + (size_t)p0 * fs : nullptr);
             if (rc) return rc;
+            if (pk && (rc = launch_pack(ctx, sc, p->H, p->W, np, (const int8_t *)d_coef + (size_t)p0 * npix * 3,
+                                        d_bitmap + (size_t)p0 * rows_per_p * nbx8, d_rowcnt + (size_t)p0 * rows_per_p,
+                                        d_rowoff + (size_t)p0 * rows_per_p, d_values, d_total, d_total + 1 + c)))
+                return rc;
         }
         CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sc));
         CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->chunk_events[2 * c + 1], 0));
+        if (pk && np > 0) {
+            // the stream length first (8 bytes): the host needs it before it can size the value download, which is
+            // queued one segment later so that the compute stream never waits for the host
+            CK(ctx, cudaMemcpyAsync(&ctx->h_segend[c], d_total + 1 + c, 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(ctx, cudaEventRecord(ctx->seg_events[c], ctx->s_d2h));
+            CK(ctx, cudaMemcpyAsync(pk->bitmap + (size_t)p0 * rows_per_p * nbx8, d_bitmap + (size_t)p0 * rows_per_p * nbx8,
+                                    (size_t)np * rows_per_p * nbx8 * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(ctx, cudaMemcpyAsync(pk->row_count + (size_t)p0 * rows_per_p, d_rowcnt + (size_t)p0 * rows_per_p,
+                                    (size_t)np * rows_per_p * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if ((rc = drain_values(c))) return rc;        // segments before this one
+        }
         if (np > 0) {
             if (mv) CK(ctx, cudaMemcpyAsync(mv + (size_t)p0 * N * 2, d_mv + (size_t)p0 * N * 2, (size_t)np * N * 4,
                                             cudaMemcpyDeviceToHost, ctx->s_d2h));
@@ -880,6 +976,7 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
         }
         p0 += np;
     }
+    if (pk) return drain_values(nsegs);
     return VCS_OK;
     };
     rc = pipeline();
@@ -887,6 +984,107 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
     cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(sc), e3 = cudaStreamSynchronize(ctx->s_d2h);
     if (rc) return rc;
     CK(ctx, e1); CK(ctx, e2); CK(ctx, e3);
+    return pending_device_error(ctx);
+}
+
+int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
+                         int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef,
+                         uint8_t *recon) {
+    return encode_clip_host_impl(ctx, p, frames, T, gop_len, coef_mode, mv, cost, flags, coef, recon, nullptr);
+}
+
+int vcs_encode_clip_host_packed(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
+                                int16_t *mv, uint32_t *cost, uint8_t *flags, uint64_t *bitmap, uint32_t *row_count,
+                                int8_t *values, size_t values_capacity, uint64_t *nvalues, uint8_t *recon) {
+    if (!ctx) return VCS_E_INVALID;
+    if (!bitmap || !row_count || !values || !nvalues) return fail(ctx, VCS_E_INVALID, "NULL packed output");
+    PackedHost pk{(unsigned long long *)bitmap, row_count, values, values_capacity, (unsigned long long *)nvalues};
+    return encode_clip_host_impl(ctx, p, frames, T, gop_len, VCS_COEF_I8_RINT, mv, cost, flags, nullptr, recon, &pk);
+}
+
+// dense int8 index planes [nP][3][H][W] (device) -> packed form (device): bitmap [nP][3][H/8][W/8], row_count
+// [nP][3][H/8], values (capacity 3*H*W*nP bytes is always enough), *nvalues_host = stream length (synchronises).
+int vcs_pack_coef_dev(vcs_ctx *ctx, int H, int W, int nP, const int8_t *coef, uint64_t *bitmap, uint32_t *row_count,
+                      int8_t *values, uint64_t *nvalues_host) {
+    VCS_ENTER(ctx);
+    if (!coef || !bitmap || !row_count || !values || !nvalues_host || H <= 0 || W <= 0 || H % 8 || W % 8 || nP < 0)
+        return fail(ctx, VCS_E_INVALID, "bad pack arguments");
+    if (((uintptr_t)coef | (uintptr_t)bitmap) & 7) return fail(ctx, VCS_E_INVALID, "coef and bitmap must be 8-byte aligned");
+    unsigned long long *d_rowoff, *d_total; int rc;
+    const int nrows = nP * 3 * (H / 8);
+    if ((rc = dev_buf(ctx, S_PK_ROWOFF, (size_t)nrows * 8 + 8, (void **)&d_rowoff))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_TOTAL, 8, (void **)&d_total))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemsetAsync(d_total, 0, 8, st));
+    if ((rc = launch_pack(ctx, st, H, W, nP, coef, (unsigned long long *)bitmap, row_count, d_rowoff, values, d_total, nullptr)))
+        return rc;
+    unsigned long long tot = 0;
+    CK(ctx, cudaMemcpyAsync(&tot, d_total, 8, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    *nvalues_host = tot;
+    return VCS_OK;
+}
+
+// the exact inverse, all device pointers; enqueued on the context's stream
+int vcs_unpack_coef_dev(vcs_ctx *ctx, int H, int W, int nP, const uint64_t *bitmap, const uint32_t *row_count,
+                        const int8_t *values, uint64_t nvalues, int8_t *coef) {
+    VCS_ENTER(ctx);
+    if (!coef || !bitmap || !row_count || (!values && nvalues) || H <= 0 || W <= 0 || H % 8 || W % 8 || nP < 0)
+        return fail(ctx, VCS_E_INVALID, "bad unpack arguments");
+    if (((uintptr_t)coef | (uintptr_t)bitmap) & 7) return fail(ctx, VCS_E_INVALID, "coef and bitmap must be 8-byte aligned");
+    unsigned long long *d_rowoff, *d_total; int rc;
+    const int nrows = nP * 3 * (H / 8);
+    if (nrows == 0) return VCS_OK;
+    if ((rc = dev_buf(ctx, S_PK_ROWOFF, (size_t)nrows * 8 + 8, (void **)&d_rowoff))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_TOTAL, 8, (void **)&d_total))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemsetAsync(d_total, 0, 8, st));
+    pack_scan_kernel<<<1, 1024, 0, st>>>(row_count, nrows, d_rowoff, d_total, nullptr);
+    unpack_kernel<<<pack_grid(ctx, nrows), 32 * PACK_WARPS, 0, st>>>((const unsigned long long *)bitmap, d_rowoff, values,
+                                                                    nvalues, W, nrows, coef, ctx->h_errflag);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return VCS_OK;
+}
+
+// Decoder side from the packed form, host buffers: upload, unpack, then vcs_decode_clip_dev's kernel.
+int vcs_decode_clip_host_packed(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_frames, int T, int gop_len,
+                                const int16_t *mv, const uint64_t *bitmap, const uint32_t *row_count,
+                                const int8_t *values, uint64_t nvalues, uint8_t *recon) {
+    VCS_ENTER(ctx);
+    if (!ref_frames || !mv || !bitmap || !row_count || !recon || gop_len < 2 || T < 1 || bs <= 0 || H < bs || W < bs)
+        return fail(ctx, VCS_E_INVALID, "bad decode arguments");
+    if (H % 8 || W % 8) return fail(ctx, VCS_E_INVALID, "H=%d W=%d must be multiples of 8", H, W);
+    const size_t fs = (size_t)H * W * 3, npix = (size_t)H * W;
+    const int N = vcs_num_blocks(H, W, bs), nP = vcs_num_p_frames(T, gop_len), nG = (T + gop_len - 1) / gop_len;
+    for (long long k = 0; k < (long long)nP * N; ++k) {
+        const int b = (int)(k % N);
+        const int x = (b % (W / bs)) * bs + mv[2 * k], y = (b / (W / bs)) * bs + mv[2 * k + 1];
+        if (x < 0 || y < 0 || x + bs > W || y + bs > H)
+            return fail(ctx, VCS_E_INVALID, "motion vector %lld points outside the frame", k);
+    }
+    const size_t nrows = (size_t)nP * 3 * (H / 8), nbx8 = W / 8;
+    unsigned long long tot = 0;
+    for (size_t k = 0; k < nrows; ++k) tot += row_count[k];
+    if (tot != nvalues) return fail(ctx, VCS_E_INVALID, "row counts (%llu) do not add up to the stream length (%llu)", tot, (unsigned long long)nvalues);
+    uint8_t *d_ref, *d_rec; int16_t *d_mv; int8_t *d_coef, *d_values; unsigned long long *d_bitmap; uint32_t *d_rowcnt; int rc;
+    if ((rc = dev_buf(ctx, S_FRAMES, fs * nG, (void **)&d_ref))) return rc;
+    if ((rc = dev_buf(ctx, S_MV, (size_t)nP * N * 4 + 4, (void **)&d_mv))) return rc;
+    if ((rc = dev_buf(ctx, S_COEF, (size_t)nP * npix * 3 + 8, (void **)&d_coef))) return rc;
+    if ((rc = dev_buf(ctx, S_RECON, (size_t)nP * fs + 4, (void **)&d_rec))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_BITMAP, nrows * nbx8 * 8 + 8, (void **)&d_bitmap))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_ROWCNT, nrows * 4 + 4, (void **)&d_rowcnt))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_VALUES, (size_t)nvalues + 64, (void **)&d_values))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemcpyAsync(d_ref, ref_frames, fs * nG, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(d_mv, mv, (size_t)nP * N * 4, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(d_bitmap, bitmap, nrows * nbx8 * 8, cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(d_rowcnt, row_count, nrows * 4, cudaMemcpyHostToDevice, st));
+    if (nvalues) CK(ctx, cudaMemcpyAsync(d_values, values, (size_t)nvalues, cudaMemcpyHostToDevice, st));
+    if ((rc = vcs_unpack_coef_dev(ctx, H, W, nP, (const uint64_t *)d_bitmap, d_rowcnt, d_values, nvalues, d_coef))) return rc;
+    if ((rc = vcs_decode_clip_dev(ctx, H, W, bs, d_ref, T, gop_len, d_mv, VCS_COEF_I8_RINT, d_coef, d_rec))) return rc;
+    CK(ctx, cudaMemcpyAsync(recon, d_rec, (size_t)nP * fs, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
     return pending_device_error(ctx);
 }
 

@@ -50,3 +50,43 @@ def gather_p_outputs(local, T, gop_len, dist, device=None):
         dist.all_gather(bufs, raw)
         out[name] = torch.cat([b.view(t.dtype).reshape(pad.shape)[:c] for b, c in zip(bufs, counts)], 0)
     return out
+
+
+class GatherPlan:
+    """all_gather of per-P-frame tensors with buffers allocated ONCE (bench.py's C3 leg gathers gigabytes per step; the
+    pad/cat temporaries of gather_p_outputs would dominate).  gather() returns per-rank views in clip order."""
+
+    def __init__(self, like, T, gop_len, dist):
+        import torch
+        self.dist, self.world, self.rank = dist, dist.get_world_size(), dist.get_rank()
+        self.counts = []
+        for r in range(self.world):
+            t0, t1 = frame_range(T, gop_len, r, self.world)
+            self.counts.append(p_count(t1 - t0, gop_len))
+        mx = max(self.counts)
+        self.shapes, self.recv, self.send = {}, {}, {}
+        for name, t in like.items():
+            per = int(t[0].numel()) * t.element_size() if t.shape[0] else 0
+            self.shapes[name] = (tuple(t.shape[1:]), t.dtype, per)
+            self.recv[name] = torch.empty((self.world, mx * per), dtype=torch.uint8, device=t.device)
+            self.send[name] = torch.zeros(mx * per, dtype=torch.uint8, device=t.device) if self.counts[self.rank] < mx else None
+
+    def bytes_per_step(self):
+        return sum(int(self.recv[n].numel()) for n in self.recv)
+
+    def gather(self, local):
+        out = {}
+        for name, t in local.items():
+            shape, dtype, per = self.shapes[name]
+            raw = t.reshape(-1).view(self.dist_uint8())
+            if self.send[name] is not None:          # shorter shard: pad to the common length
+                self.send[name][:raw.numel()] = raw
+                raw = self.send[name]
+            self.dist.all_gather_into_tensor(self.recv[name].view(-1), raw)
+            out[name] = [self.recv[name][r, :c * per].view(dtype).reshape((c,) + shape) for r, c in enumerate(self.counts)]
+        return out
+
+    @staticmethod
+    def dist_uint8():
+        import torch
+        return torch.uint8

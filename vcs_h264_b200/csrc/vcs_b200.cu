@@ -40,7 +40,7 @@ struct EvTriple {
 struct vcs_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_aux = nullptr;
     char err[512] = {0};
     double h_Q[192];
     double *d_Q = nullptr;
@@ -445,6 +445,7 @@ int vcs_create(int device, vcs_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&ctx->d_Q, sizeof(ctx->h_Q)) != cudaSuccess ||
         cudaHostAlloc((void **)&ctx->h_errflag, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaMemcpyToSymbol(c_dct, C, sizeof(C)) != cudaSuccess ||
@@ -474,6 +475,7 @@ int vcs_destroy(vcs_ctx *ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
     delete ctx;
     return VCS_OK;
 }
@@ -906,19 +908,22 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
     // (Running consecutive searches on two streams so that one fills the other's tail was tried and is slower:
     // the persistent search CTAs of the next chunk then keep the DCT stage of this chunk off the SMs.)
     cudaStream_t sc = ctx->stream;
-    unsigned long long host_values = 0;      // bytes of the value stream already queued for download
-    int seg_done = 0;                        // segments whose values have been queued
-    auto drain_values = [&](int upto) -> int {   // queue the value downloads of segments [seg_done, upto)
-        for (; seg_done < upto; ++seg_done) {
-            CK(ctx, cudaEventSynchronize(ctx->seg_events[seg_done]));     // its stream length has landed
-            const unsigned long long end = ctx->h_segend[seg_done];
-            if (end > pk->capacity) return fail(ctx, VCS_E_INVALID, "value buffer too small (%llu > %zu bytes)", end, pk->capacity);
-            if (end > host_values)
-                CK(ctx, cudaMemcpyAsync(pk->values + host_values, d_values + host_values, end - host_values,
+    // Pass 1 queues everything that does not depend on what the host knows: uploads, kernels and -- without the packed
+    // sink -- the downloads.  With the packed sink the size of a segment's value stream is only known once its scan
+    // kernel has run, so each segment just sends that length (8 bytes, own stream: it must not queue behind the
+    // uploads or the other downloads) and pass 2 queues a segment's downloads as soon as its length has landed.
+    auto download = [&](int p0, int np) -> int {
+        if (mv) CK(ctx, cudaMemcpyAsync(mv + (size_t)p0 * N * 2, d_mv + (size_t)p0 * N * 2, (size_t)np * N * 4,
                                         cudaMemcpyDeviceToHost, ctx->s_d2h));
-            host_values = end;
-        }
-        *pk->nvalues = host_values;
+        if (cost) CK(ctx, cudaMemcpyAsync(cost + (size_t)p0 * N, d_cost + (size_t)p0 * N, (size_t)np * N * 4,
+                                          cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (flags) CK(ctx, cudaMemcpyAsync(flags + (size_t)p0 * N, d_fl + (size_t)p0 * N, (size_t)np * N,
+                                           cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (coef) CK(ctx, cudaMemcpyAsync((char *)coef + (size_t)p0 * npix * 3 * ce,
+                                          (char *)d_coef + (size_t)p0 * npix * 3 * ce,
+                                          (size_t)np * npix * 3 * ce, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (recon) CK(ctx, cudaMemcpyAsync(recon + (size_t)p0 * fs, d_rec + (size_t)p0 * fs, (size_t)np * fs,
+                                           cudaMemcpyDeviceToHost, ctx->s_d2h));
         return VCS_OK;
     };
     auto pipeline = [&]() -> int {
@@ -949,41 +954,46 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
                 return rc;
         }
         CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sc));
-        CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->chunk_events[2 * c + 1], 0));
-        if (pk && np > 0) {
-            // the stream length first (8 bytes): the host needs it before it can size the value download, which is
-            // queued one segment later so that the compute stream never waits for the host
-            CK(ctx, cudaMemcpyAsync(&ctx->h_segend[c], d_total + 1 + c, 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
-            CK(ctx, cudaEventRecord(ctx->seg_events[c], ctx->s_d2h));
+        if (pk) {
+            CK(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->chunk_events[2 * c + 1], 0));
+            CK(ctx, cudaMemcpyAsync(&ctx->h_segend[c], d_total + 1 + c, 8, cudaMemcpyDeviceToHost, ctx->s_aux));
+            CK(ctx, cudaEventRecord(ctx->seg_events[c], ctx->s_aux));
+        } else {
+            CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->chunk_events[2 * c + 1], 0));
+            if (np > 0 && (rc = download(p0, np))) return rc;
+        }
+        p0 += np;
+    }
+    if (!pk) return VCS_OK;
+    unsigned long long host_values = 0;      // bytes of the value stream already queued for download
+    p0 = 0;
+    for (int c = 0; c < nsegs; ++c) {
+        const int np = sizes[c];
+        CK(ctx, cudaEventSynchronize(ctx->seg_events[c]));       // segment c is complete and its stream length is here
+        const unsigned long long end = ctx->h_segend[c];
+        if (end > pk->capacity) return fail(ctx, VCS_E_INVALID, "value buffer too small (%llu > %zu bytes)", end, pk->capacity);
+        if (np > 0) {
+            if (end > host_values)
+                CK(ctx, cudaMemcpyAsync(pk->values + host_values, d_values + host_values, end - host_values,
+                                        cudaMemcpyDeviceToHost, ctx->s_d2h));
             CK(ctx, cudaMemcpyAsync(pk->bitmap + (size_t)p0 * rows_per_p * nbx8, d_bitmap + (size_t)p0 * rows_per_p * nbx8,
                                     (size_t)np * rows_per_p * nbx8 * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
             CK(ctx, cudaMemcpyAsync(pk->row_count + (size_t)p0 * rows_per_p, d_rowcnt + (size_t)p0 * rows_per_p,
                                     (size_t)np * rows_per_p * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
-            if ((rc = drain_values(c))) return rc;        // segments before this one
+            if ((rc = download(p0, np))) return rc;
         }
-        if (np > 0) {
-            if (mv) CK(ctx, cudaMemcpyAsync(mv + (size_t)p0 * N * 2, d_mv + (size_t)p0 * N * 2, (size_t)np * N * 4,
-                                            cudaMemcpyDeviceToHost, ctx->s_d2h));
-            if (cost) CK(ctx, cudaMemcpyAsync(cost + (size_t)p0 * N, d_cost + (size_t)p0 * N, (size_t)np * N * 4,
-                                              cudaMemcpyDeviceToHost, ctx->s_d2h));
-            if (flags) CK(ctx, cudaMemcpyAsync(flags + (size_t)p0 * N, d_fl + (size_t)p0 * N, (size_t)np * N,
-                                               cudaMemcpyDeviceToHost, ctx->s_d2h));
-            if (coef) CK(ctx, cudaMemcpyAsync((char *)coef + (size_t)p0 * npix * 3 * ce,
-                                              (char *)d_coef + (size_t)p0 * npix * 3 * ce,
-                                              (size_t)np * npix * 3 * ce, cudaMemcpyDeviceToHost, ctx->s_d2h));
-            if (recon) CK(ctx, cudaMemcpyAsync(recon + (size_t)p0 * fs, d_rec + (size_t)p0 * fs, (size_t)np * fs,
-                                               cudaMemcpyDeviceToHost, ctx->s_d2h));
-        }
+        host_values = end;
+        *pk->nvalues = host_values;
         p0 += np;
     }
-    if (pk) return drain_values(nsegs);
     return VCS_OK;
     };
     rc = pipeline();
     // success or not, nothing may still be reading or writing the caller's buffers when this returns
-    cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(sc), e3 = cudaStreamSynchronize(ctx->s_d2h);
+    cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(sc), e3 = cudaStreamSynchronize(ctx->s_d2h),
+                e4 = cudaStreamSynchronize(ctx->s_aux);
     if (rc) return rc;
-    CK(ctx, e1); CK(ctx, e2); CK(ctx, e3);
+    CK(ctx, e1); CK(ctx, e2); CK(ctx, e3); CK(ctx, e4);
     return pending_device_error(ctx);
 }
 

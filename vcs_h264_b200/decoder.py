@@ -1,8 +1,12 @@
 """Decoder -- drop-in for InterframeCompression/decoder.py:11-69."""
 from __future__ import annotations
 
+import numpy as np
+
+from . import _capi
 from .DCTcompressor import DCTCompressor
-from .motion import MotionProcessor
+from .motion import WRITE_STATIC_BLOCK, MotionProcessor, _as_frame
+from .runtime import get_context
 
 WRITE_REF_FRAMES = True
 
@@ -56,8 +60,44 @@ class Decoder:
 
     def _reconstruct_P_frame(self, cur_frame, with_residuals):
         ref = self.ref_frames[cur_frame.ref_i]
+        if with_residuals and self.with_DCT and self.DCTCompressor.blocksize == 8:
+            fused = self._reconstruct_P_frame_fused(cur_frame, ref)
+            if fused is not None:
+                return fused
         reconstruct_img = self.MotionProcessor.reconstruct_from_motion_vectors(
             cur_frame.mv, ref, cur_frame.c)
         if with_residuals:
             return self._fully_reconstruct(residuals=cur_frame.r, img=reconstruct_img)
         return reconstruct_img
+
+    def _reconstruct_P_frame_fused(self, cur_frame, ref):
+        """decoder.py:52-69 as ONE C-ABI call (vcs_decode_clip_host on a one-P-frame clip): motion compensation from
+        the original I-frame, dequantise, IDCT, truncating store, YCrCb->BGR and the wrap add on the device."""
+        mp, dc = self.MotionProcessor, self.DCTCompressor
+        H, W, bs = int(mp.shape[0]), int(mp.shape[1]), int(mp.block_size)
+        first = np.asarray(cur_frame.r[0])
+        if first.shape != (H, W) or H % 8 or W % 8:
+            return None                                    # geometry the step-by-step path handles (or refuses)
+        want = mp._block_coords()
+        coords = np.asarray(cur_frame.c, np.int64).reshape(-1, 2)
+        if coords.shape != want.shape or not np.array_equal(coords, want):
+            raise ValueError("block_coords must be the raster grid of _split_frame_into_mblocks")
+        mv = np.asarray(cur_frame.mv, np.int64).reshape(-1, 2)
+        if mv.shape[0] != want.shape[0]:
+            raise ValueError("one motion vector per macroblock expected")
+        mv16 = np.ascontiguousarray(mv.astype(np.int16))
+        if first.dtype == np.int16:
+            planes, mode = np.ascontiguousarray(np.stack(cur_frame.r).astype(np.int16)), _capi.COEF_I16_RINT
+        else:
+            planes, mode = np.ascontiguousarray(np.stack(cur_frame.r).astype(np.float64)), _capi.COEF_F64
+        refc = np.ascontiguousarray(_as_frame(ref, mp.shape, "ref_frame"))
+        out = np.empty((H, W, 3), np.uint8)
+        ctx = get_context(mp._device)
+        ctx.set_q(np.stack([np.asarray(q, np.float64) for q in dc.Q]))
+        ctx.call("vcs_decode_clip_host", H, W, bs, refc.ctypes.data, 2, 2, mv16.ctypes.data, mode, planes.ctypes.data,
+                 out.ctypes.data)
+        num_static = int(np.count_nonzero((mv[:, 0] == 0) & (mv[:, 1] == 0))) if WRITE_STATIC_BLOCK else 0
+        print("There are", num_static, "static blocks out of", len(coords), "blocks")  # motion.py:67
+        print("begin decompression")                                                     # DCTcompressor.py:78
+        print("decompression finished")                                                  # DCTcompressor.py:90
+        return out

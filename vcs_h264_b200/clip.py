@@ -11,7 +11,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _capi
-from .runtime import get_context
+from .runtime import acquire_context, release_context
 
 COEF_DTYPES = {_capi.COEF_F64: np.float64, _capi.COEF_F64_RINT: np.float64,
                _capi.COEF_I16_RINT: np.int16, _capi.COEF_I8_RINT: np.int8}
@@ -45,9 +45,19 @@ class ClipEncoder:
         self.coef_mode = coef_mode
         self.device = device
         # own context: its Q tables, stream and scratch are not shared with other front-ends on the device
-        self.ctx = _capi.Context(device)
+        self.ctx = acquire_context(device)
         self.Q = _capi.q_tables(qf)
         self.ctx.set_q(self.Q)
+
+    def close(self):
+        ctx, self.ctx = getattr(self, "ctx", None), None
+        release_context(ctx)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def num_p_frames(self, T):
         return _capi.num_p_frames(T, self.gop_len)
@@ -171,9 +181,19 @@ class ClipDecoder:
     def __init__(self, shape, block_size=16, gop_len=4, qf=50.0, coef_mode=_capi.COEF_I16_RINT, device=0):
         self.H, self.W, self.bs, self.gop_len = int(shape[0]), int(shape[1]), block_size, gop_len
         self.coef_mode, self.device = coef_mode, device
-        self.ctx = _capi.Context(device)           # own context, like ClipEncoder
+        self.ctx = acquire_context(device)         # own context, like ClipEncoder
         self.Q = _capi.q_tables(qf)
         self.ctx.set_q(self.Q)
+
+    def close(self):
+        ctx, self.ctx = getattr(self, "ctx", None), None
+        release_context(ctx)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def decode_host(self, ref_frames, mv, coef, T):
         """ref_frames uint8 [nG,H,W,3] (the I-frames), mv int16 [nP,N,2], coef [nP,3,H,W] -> uint8 [nP,H,W,3]."""

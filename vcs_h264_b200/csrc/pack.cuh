@@ -97,11 +97,16 @@ pack_scan_kernel(const uint32_t *__restrict__ row_count, int n, unsigned long lo
     if (threadIdx.x == 0) { *total = carry; if (seg_end) *seg_end = carry; }
 }
 
-// values of block row `row` start at values[row_off[row]]; lanes = blocks, a warp-wide prefix of the popcounts places them
+// values of block row `row` start at values[row_off[row]]; lanes = blocks, a warp-wide prefix of the popcounts places
+// them.  A lane's values are a byte string at an arbitrary byte offset: written straight to global memory every store
+// instruction would touch 32 different sectors, so the warp first compacts its 32 blocks into shared memory and then
+// streams the contiguous run (<= 2 KB) out with one sector per store instruction.
 __global__ void __launch_bounds__(32 * PACK_WARPS)
 pack_write_kernel(const int8_t *__restrict__ coef, int W, int nrows, const unsigned long long *__restrict__ row_off,
                   int8_t *__restrict__ values) {
+    __shared__ __align__(16) uint8_t stage[PACK_WARPS][32 * 64 + 16];
     const int lane = threadIdx.x & 31, nbx = W / 8;
+    uint8_t *sw = stage[threadIdx.x >> 5];
     for (int row = blockIdx.x * PACK_WARPS + (threadIdx.x >> 5); row < nrows; row += gridDim.x * PACK_WARPS) {
         const int8_t *base = coef + (size_t)row * 8 * W;
         unsigned long long off = row_off[row];
@@ -117,19 +122,24 @@ pack_write_kernel(const int8_t *__restrict__ coef, int W, int nrows, const unsig
                 const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
-            int8_t *dst = values + off + (incl - cnt);
-            if (bx < nbx) {
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (cnt) {
+                uint8_t *dst = sw + (incl - cnt);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const uint32_t w[2] = {rows[i].x, rows[i].y};
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                        if (b) *dst++ = (int8_t)b;
+                        if (b) *dst++ = (uint8_t)b;
                     }
                 }
             }
-            off += __shfl_sync(0xffffffffu, incl, 31);
+            __syncwarp();
+            int8_t *g = values + off;
+            for (uint32_t k = lane; k < total; k += 32) g[k] = (int8_t)sw[k];
+            __syncwarp();
+            off += total;
         }
     }
 }

@@ -11,6 +11,21 @@ from .runtime import get_context
 WRITE_REF_FRAMES = True
 
 
+def _planes_block(r, dtype):
+    """The three planes as one C-contiguous [3,H,W] array without copying when they already are three consecutive
+    slices of one (that is how the drop-in Encoder leaves them); otherwise one stacking copy."""
+    a, b, c = (np.asarray(x) for x in r[:3])
+    base = a.base
+    if (base is not None and b.base is base and c.base is base and isinstance(base, np.ndarray) and base.dtype == dtype
+            and base.shape == (3,) + a.shape and base.flags["C_CONTIGUOUS"]
+            and a.ctypes.data == base.ctypes.data and b.ctypes.data == base[1].ctypes.data
+            and c.ctypes.data == base[2].ctypes.data):
+        return base
+    out = np.empty((3,) + a.shape, dtype)
+    out[0], out[1], out[2] = a, b, c
+    return out
+
+
 def _fourcc(code):
     """cv2.VideoWriter_fourcc(*code) without needing OpenCV at construction time (same little-endian packing)."""
     return sum(ord(c) << (8 * i) for i, c in enumerate(code))
@@ -86,10 +101,8 @@ class Decoder:
         if mv.shape[0] != want.shape[0]:
             raise ValueError("one motion vector per macroblock expected")
         mv16 = np.ascontiguousarray(mv.astype(np.int16))
-        if first.dtype == np.int16:
-            planes, mode = np.ascontiguousarray(np.stack(cur_frame.r).astype(np.int16)), _capi.COEF_I16_RINT
-        else:
-            planes, mode = np.ascontiguousarray(np.stack(cur_frame.r).astype(np.float64)), _capi.COEF_F64
+        mode = _capi.COEF_I16_RINT if first.dtype == np.int16 else _capi.COEF_F64
+        planes = _planes_block(cur_frame.r, np.int16 if mode == _capi.COEF_I16_RINT else np.float64)
         refc = np.ascontiguousarray(_as_frame(ref, mp.shape, "ref_frame"))
         out = np.empty((H, W, 3), np.uint8)
         ctx = get_context(mp._device)

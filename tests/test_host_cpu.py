@@ -167,6 +167,39 @@ print("OK", r)
     assert r.stdout.count("OK") == 2
 
 
+def test_gather_plan_world2_gloo(tmp_path):
+    """GatherPlan (bench.py's C3 leg): preallocated all_gather of unequal shards, per-rank views in clip order."""
+    script = tmp_path / "w2.py"
+    script.write_text(f"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {ROOT!r})
+from vcs_h264_b200 import sharding
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+T, g = 22, 4                                   # 6 GOPs (the last one short): 3 + 3 GOPs, 9 + 7 P-frames
+t0, t1 = sharding.frame_range(T, g, r, w)
+ps = [t for t in range(t0, t1) if t % g]
+local = dict(mv=torch.tensor(ps, dtype=torch.int16).reshape(-1, 1, 1).repeat(1, 5, 2).contiguous(),
+             coef=torch.tensor(ps, dtype=torch.int8).reshape(-1, 1, 1, 1).repeat(1, 3, 4, 8).contiguous())
+plan = sharding.GatherPlan(local, T, g, dist)
+for _ in range(2):                             # buffers are reused
+    out = plan.gather(local)
+want = [t for t in range(T) if t % g]
+got = torch.cat(out["mv"], 0)[:, 0, 0].tolist()
+assert got == want, got
+assert torch.cat(out["coef"], 0)[:, 2, 3, 7].tolist() == want
+assert [x.shape[0] for x in out["mv"]] == plan.counts and sum(plan.counts) == len(want)
+dist.destroy_process_group()
+print("OK", r)
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29513")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29513", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("OK") == 2
+
+
 def test_only_tests_bench_and_smoke_touch_the_oracle():
     """oracle/ is test infrastructure: nothing under the product package or tools/ may import it."""
     import glob

@@ -58,6 +58,12 @@ __device__ __forceinline__ uint32_t bytesum_acc(uint32_t a, uint32_t acc) {
     return __dp4a(a, 0x01010101u, acc);
 }
 
+// occupancy nibble of one word: bit k = (byte k != 0)
+__device__ __forceinline__ uint32_t nz_nibble(uint32_t x) {
+    const uint32_t nz = (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;   // bit 7 of every non-zero byte
+    return (((nz >> 7) * 0x01020408u) >> 24) & 0xfu;                              // gather bits 0,8,16,24 -> 0..3
+}
+
 template <int METRIC>
 __device__ __forceinline__ uint32_t cost4_acc(uint32_t r, uint32_t c, uint32_t acc) {
     if (METRIC == 0) return wrap4_acc(r, c, acc);

@@ -68,6 +68,10 @@ struct DctArgs {
     const uint8_t *pred_in;  // inverse-only: optional pred image to add (decoder.py:57)
     uint8_t *recon;          // [nP][H][W][3] or nullptr
     int *err;                // mapped host flag: set when a motion vector points outside the frame
+    // packed sink (pack.cuh), int8 mode only: per 8x8 block its occupancy bitmap (8 bytes, byte i = row i) and per
+    // block row the number of non-zero indices (accumulated with atomics: zero it before the launch); may be null
+    uint8_t *bitmap;         // [nP][3][H/8][W/8][8]
+    uint32_t *row_count;     // [nP][3][H/8]
 };
 
 // 24 bytes (8 BGR pixels) starting at an arbitrary byte address, as 6 words
@@ -243,6 +247,9 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
             }
             __syncwarp();
             // ---- C: row pass  D = T . C^T  (D[i][j] = sum_k T[i][k] C[j][k]); quantise; store ------------
+            uint32_t nnz_lane[DCT_NCH];
+#pragma unroll
+            for (int c = 0; c < DCT_NCH; ++c) nnz_lane[c] = 0;
             if (row_on) {
                 double tk[DCT_NCH][8];
 #pragma unroll
@@ -269,10 +276,10 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                 for (int c = 0; c < DCT_NCH; ++c) {
                     const int ch = ch0 + c;
                     bool exact = coef_mode == 0;        // un-rounded mode: np.true_divide (DCTcompressor.py:71)
+                    uint32_t pk[4];
 #pragma unroll 1
                     for (int attempt = 0; attempt < 2; ++attempt) {
                         bool near_half = false;
-                        uint32_t pk[4];
                         double dprev = 0.0;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -312,6 +319,21 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                         if (exact || !near_half) break;   // per lane; the second attempt redoes this lane's row exactly
                         exact = true;
                     }
+                    if (PATH == DCT_FWD && coef_mode == 3 && a.bitmap) {
+                        // occupancy of this lane's 8 indices = byte rp_i of the block's bitmap; 32 lanes = 32 consecutive bytes
+                        const uint32_t m8 = nz_nibble(pk[0]) | (nz_nibble(pk[1]) << 4);
+                        a.bitmap[(((size_t)p * 3 + ch) * (H / 8) + ty) * (size_t)(W / 8) * 8 + (size_t)(tx * 4 + rp_blk) * 8 + rp_i] = (uint8_t)m8;
+                        nnz_lane[c] = __popc(m8);
+                    }
+                }
+            }
+            if (PATH == DCT_FWD && coef_mode == 3 && a.bitmap) {       // warp-uniform: every lane takes part in the reduction
+#pragma unroll
+                for (int c = 0; c < DCT_NCH; ++c) {
+                    uint32_t n = nnz_lane[c];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+                    if (lane == 0 && n) atomicAdd(a.row_count + ((size_t)p * 3 + ch0 + c) * (H / 8) + ty, n);
                 }
             }
         } else if (do_inverse && row_on) {

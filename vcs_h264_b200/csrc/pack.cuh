@@ -10,7 +10,8 @@
 //   dense : 3*H*W bytes per P-frame           packed : 3*H*W/8 (bitmaps) + nnz (values) + 12*H/8 (row counts)
 //
 // Kernels (HBM-bound streaming passes, one warp per block row, lanes = blocks, every load coalesced):
-//   pack_count_kernel   dense int8 planes -> bitmaps + row counts
+//   pack_count_kernel   dense int8 planes -> bitmaps + row counts (stand-alone packing; in the encoder the DCT stage
+//                       emits both while it still holds the indices in registers, dct_stage.cuh)
 //   pack_scan_kernel    exclusive prefix of the row counts of one segment (single CTA) + running clip total
 //   pack_write_kernel   dense planes + bitmaps + row offsets -> value stream
 //   unpack_kernel       the exact inverse (decoder side)
@@ -18,12 +19,6 @@
 #include "common.cuh"
 
 namespace vcs {
-
-// occupancy nibble of one word: bit k = (byte k != 0)
-__device__ __forceinline__ uint32_t nz_nibble(uint32_t x) {
-    const uint32_t nz = (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;   // bit 7 of every non-zero byte
-    return (((nz >> 7) * 0x01020408u) >> 24) & 0xfu;                              // gather bits 0,8,16,24 -> 0..3
-}
 
 // bitmap of the 8x8 block whose top-left byte is p (row pitch W); p is 8-byte aligned
 __device__ __forceinline__ unsigned long long block_bitmap(const int8_t *p, int W, uint2 rows[8]) {
@@ -97,37 +92,44 @@ pack_scan_kernel(const uint32_t *__restrict__ row_count, int n, unsigned long lo
     if (threadIdx.x == 0) { *total = carry; if (seg_end) *seg_end = carry; }
 }
 
-// values of block row `row` start at values[row_off[row]]; lanes = blocks, a warp-wide prefix of the popcounts places
-// them.  A lane's values are a byte string at an arbitrary byte offset: written straight to global memory every store
+// One warp per (block row, batch of 32 blocks).  The batch's values start at row_off[row] + the popcount of the row's
+// earlier bitmaps (read back, <= 7 coalesced loads per lane); lanes = blocks, a warp-wide prefix places each block.
+// A lane's values are a byte string at an arbitrary byte offset: written straight to global memory every store
 // instruction would touch 32 different sectors, so the warp first compacts its 32 blocks into shared memory and then
 // streams the contiguous run (<= 2 KB) out with one sector per store instruction.
 __global__ void __launch_bounds__(32 * PACK_WARPS)
-pack_write_kernel(const int8_t *__restrict__ coef, int W, int nrows, const unsigned long long *__restrict__ row_off,
-                  int8_t *__restrict__ values) {
+pack_write_kernel(const int8_t *__restrict__ coef, int W, int nrows, const unsigned long long *__restrict__ bitmap,
+                  const unsigned long long *__restrict__ row_off, int8_t *__restrict__ values) {
     __shared__ __align__(16) uint8_t stage[PACK_WARPS][32 * 64 + 16];
-    const int lane = threadIdx.x & 31, nbx = W / 8;
+    const int lane = threadIdx.x & 31, nbx = W / 8, nbatch = (nbx + 31) / 32;
     uint8_t *sw = stage[threadIdx.x >> 5];
-    for (int row = blockIdx.x * PACK_WARPS + (threadIdx.x >> 5); row < nrows; row += gridDim.x * PACK_WARPS) {
-        const int8_t *base = coef + (size_t)row * 8 * W;
-        unsigned long long off = row_off[row];
-        for (int bx0 = 0; bx0 < nbx; bx0 += 32) {
-            const int bx = bx0 + lane;
-            uint2 rows[8];
-            unsigned long long bm = 0;
-            if (bx < nbx) bm = block_bitmap(base + 8 * bx, W, rows);
-            const uint32_t cnt = __popcll(bm);
-            uint32_t incl = cnt;
+    const long long nitems = (long long)nrows * nbatch;
+    for (long long item = (long long)blockIdx.x * PACK_WARPS + (threadIdx.x >> 5); item < nitems;
+         item += (long long)gridDim.x * PACK_WARPS) {
+        const int row = (int)(item / nbatch), bx0 = (int)(item - (long long)row * nbatch) * 32;
+        const unsigned long long *bmrow = bitmap + (size_t)row * nbx;
+        uint32_t before = 0;
+        for (int b = lane; b < bx0; b += 32) before += __popcll(__ldg(bmrow + b));
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            if (cnt) {
-                uint8_t *dst = sw + (incl - cnt);
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        const int bx = bx0 + lane;
+        const unsigned long long bm = bx < nbx ? __ldg(bmrow + bx) : 0ull;
+        const uint32_t cnt = __popcll(bm);
+        uint32_t incl = cnt;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint32_t w[2] = {rows[i].x, rows[i].y};
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (cnt) {
+            const int8_t *blk = coef + (size_t)row * 8 * W + 8 * bx;
+            uint8_t *dst = sw + (incl - cnt);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if ((bm >> (8 * i)) & 0xffull) {
+                    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(blk + (size_t)i * W));
+                    const uint32_t w[2] = {r.x, r.y};
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
@@ -135,12 +137,11 @@ pack_write_kernel(const int8_t *__restrict__ coef, int W, int nrows, const unsig
                     }
                 }
             }
-            __syncwarp();
-            int8_t *g = values + off;
-            for (uint32_t k = lane; k < total; k += 32) g[k] = (int8_t)sw[k];
-            __syncwarp();
-            off += total;
         }
+        __syncwarp();
+        int8_t *g = values + row_off[row] + before;
+        for (uint32_t k = lane; k < total; k += 32) g[k] = (int8_t)sw[k];
+        __syncwarp();
     }
 }
 

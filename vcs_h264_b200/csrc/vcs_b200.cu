@@ -264,7 +264,8 @@ EvTriple *next_events(vcs_ctx *ctx) {
 
 // ME + residual/DCT/recon for nP P-frames addressed by fa, on stream st.
 int encode_dev(vcs_ctx *ctx, cudaStream_t st, const vcs_me_params *p, const FrameAddr &fa, int nP,
-               int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef, uint8_t *recon) {
+               int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef, uint8_t *recon,
+               unsigned long long *bitmap = nullptr, uint32_t *row_count = nullptr) {
     EvTriple *ev = next_events(ctx);
     if (ev) CK(ctx, cudaEventRecord(ev->e0, st));
     int rc = launch_me(ctx, st, p, fa, nP, mv, cost, flags);
@@ -276,6 +277,11 @@ int encode_dev(vcs_ctx *ctx, cudaStream_t st, const vcs_me_params *p, const Fram
         a.H = p->H; a.W = p->W; a.fa = fa; a.has_fa = 1; a.mv = mv; a.bs = p->bs;
         a.nbx = p->W / p->bs; a.nby = p->H / p->bs; a.forward = 1; a.inverse = recon != nullptr;
         a.coef_mode = coef_mode; a.coef = coef; a.recon = recon;
+        if (bitmap && row_count && coef && !recon && coef_mode == VCS_COEF_I8_RINT) {   // forward-only variant of the kernel
+            // the DCT stage emits the occupancy bitmaps and (atomically) the per-block-row counts of the packed form
+            a.bitmap = reinterpret_cast<uint8_t *>(bitmap); a.row_count = row_count;
+            CK(ctx, cudaMemsetAsync(row_count, 0, sizeof(uint32_t) * (size_t)nP * 3 * (p->H / 8), st));
+        }
         rc = launch_dct(ctx, st, a, nP);
         if (rc) return rc;
         if (ev) { CK(ctx, cudaEventRecord(ev->e2, st)); ev->has_dct = true; }
@@ -303,14 +309,18 @@ static int pack_grid(vcs_ctx *ctx, int nrows) {
 // may be null) receives the new total.
 static int launch_pack(vcs_ctx *ctx, cudaStream_t st, int H, int W, int nP, const int8_t *coef,
                        unsigned long long *d_bitmap, uint32_t *d_rowcnt, unsigned long long *d_rowoff,
-                       int8_t *d_values, unsigned long long *d_total, unsigned long long *d_segend) {
+                       int8_t *d_values, unsigned long long *d_total, unsigned long long *d_segend, bool have_bitmaps) {
     const int nrows = nP * 3 * (H / 8);
     if (nrows <= 0) return VCS_OK;
-    pack_count_kernel<<<pack_grid(ctx, nrows), 32 * PACK_WARPS, 0, st>>>(coef, W, nrows, d_bitmap, d_rowcnt);
+    const int nbatch = (W / 8 + 31) / 32;
+    if (!have_bitmaps) {     // the DCT stage did not produce them (stand-alone packing of given planes)
+        pack_count_kernel<<<pack_grid(ctx, nrows), 32 * PACK_WARPS, 0, st>>>(coef, W, nrows, d_bitmap, d_rowcnt);
+        ctx->launches += 1;
+    }
     pack_scan_kernel<<<1, 1024, 0, st>>>(d_rowcnt, nrows, d_rowoff, d_total, d_segend);
-    pack_write_kernel<<<pack_grid(ctx, nrows), 32 * PACK_WARPS, 0, st>>>(coef, W, nrows, d_rowoff, d_values);
+    pack_write_kernel<<<pack_grid(ctx, nrows * nbatch), 32 * PACK_WARPS, 0, st>>>(coef, W, nrows, d_bitmap, d_rowoff, d_values);
     CK(ctx, cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += 2;
     return VCS_OK;
 }
 
@@ -946,11 +956,13 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
             rc = encode_dev(ctx, sc, p, fa, np, coef_mode, d_mv + (size_t)p0 * N * 2, d_cost + (size_t)p0 * N,
                             d_fl + (size_t)p0 * N,
                             d_coef ? (void *)((char *)d_coef + (size_t)p0 * npix * 3 * ce) : nullptr,
-                            d_rec ? d_rec + (size_t)p0 * fs : nullptr);
+                            d_rec ? d_rec + (size_t)p0 * fs : nullptr,
+                            pk ? d_bitmap + (size_t)p0 * rows_per_p * nbx8 : nullptr,
+                            pk ? d_rowcnt + (size_t)p0 * rows_per_p : nullptr);
             if (rc) return rc;
             if (pk && (rc = launch_pack(ctx, sc, p->H, p->W, np, (const int8_t *)d_coef + (size_t)p0 * npix * 3,
                                         d_bitmap + (size_t)p0 * rows_per_p * nbx8, d_rowcnt + (size_t)p0 * rows_per_p,
-                                        d_rowoff + (size_t)p0 * rows_per_p, d_values, d_total, d_total + 1 + c)))
+                                        d_rowoff + (size_t)p0 * rows_per_p, d_values, d_total, d_total + 1 + c, d_rec == nullptr)))
                 return rc;
         }
         CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sc));
@@ -1026,7 +1038,7 @@ int vcs_pack_coef_dev(vcs_ctx *ctx, int H, int W, int nP, const int8_t *coef, ui
     if ((rc = dev_buf(ctx, S_PK_TOTAL, 8, (void **)&d_total))) return rc;
     cudaStream_t st = ctx->stream;
     CK(ctx, cudaMemsetAsync(d_total, 0, 8, st));
-    if ((rc = launch_pack(ctx, st, H, W, nP, coef, (unsigned long long *)bitmap, row_count, d_rowoff, values, d_total, nullptr)))
+    if ((rc = launch_pack(ctx, st, H, W, nP, coef, (unsigned long long *)bitmap, row_count, d_rowoff, values, d_total, nullptr, false)))
         return rc;
     unsigned long long tot = 0;
     CK(ctx, cudaMemcpyAsync(&tot, d_total, 8, cudaMemcpyDeviceToHost, st));

@@ -93,14 +93,18 @@ class Decoder:
         first = np.asarray(cur_frame.r[0])
         if first.shape != (H, W) or H % 8 or W % 8:
             return None                                    # geometry the step-by-step path handles (or refuses)
-        want = mp._block_coords()
-        coords = np.asarray(cur_frame.c, np.int64).reshape(-1, 2)
-        if coords.shape != want.shape or not np.array_equal(coords, want):
-            raise ValueError("block_coords must be the raster grid of _split_frame_into_mblocks")
-        mv = np.asarray(cur_frame.mv, np.int64).reshape(-1, 2)
-        if mv.shape[0] != want.shape[0]:
+        # block_coords must be the raster grid (motion.py:74-98).  Frames of one clip normally share one coords list:
+        # a list object that has been checked once is not converted and compared again.
+        N = (H // bs) * (W // bs)
+        if cur_frame.c is not getattr(self, "_coords_ok", None):
+            want = mp._block_coords()
+            coords = np.asarray(cur_frame.c, np.int64).reshape(-1, 2)
+            if coords.shape != want.shape or not np.array_equal(coords, want):
+                raise ValueError("block_coords must be the raster grid of _split_frame_into_mblocks")
+            self._coords_ok = cur_frame.c
+        mv16 = np.ascontiguousarray(np.asarray(cur_frame.mv, np.int16).reshape(-1, 2))
+        if mv16.shape[0] != N:
             raise ValueError("one motion vector per macroblock expected")
-        mv16 = np.ascontiguousarray(mv.astype(np.int16))
         mode = _capi.COEF_I16_RINT if first.dtype == np.int16 else _capi.COEF_F64
         planes = _planes_block(cur_frame.r, np.int16 if mode == _capi.COEF_I16_RINT else np.float64)
         refc = np.ascontiguousarray(_as_frame(ref, mp.shape, "ref_frame"))
@@ -109,8 +113,8 @@ class Decoder:
         ctx.set_q(np.stack([np.asarray(q, np.float64) for q in dc.Q]))
         ctx.call("vcs_decode_clip_host", H, W, bs, refc.ctypes.data, 2, 2, mv16.ctypes.data, mode, planes.ctypes.data,
                  out.ctypes.data)
-        num_static = int(np.count_nonzero((mv[:, 0] == 0) & (mv[:, 1] == 0))) if WRITE_STATIC_BLOCK else 0
-        print("There are", num_static, "static blocks out of", len(coords), "blocks")  # motion.py:67
+        num_static = int(np.count_nonzero((mv16[:, 0] == 0) & (mv16[:, 1] == 0))) if WRITE_STATIC_BLOCK else 0
+        print("There are", num_static, "static blocks out of", N, "blocks")             # motion.py:67
         print("begin decompression")                                                     # DCTcompressor.py:78
         print("decompression finished")                                                  # DCTcompressor.py:90
         return out

@@ -204,8 +204,9 @@ def workload_config():
                         "full search, reference cost (wrapped u8 diff) + static test thr 2000, residual, "
                         "8x8 DCT f64, quant QF50 -> int8 indices (lossless: |idx| <= 1024/min(Q) = 102)",
             "legs": {"value": "device-resident, forward + dequant, IDCT, reconstruction (outputs stay in HBM)",
-                     "e2e": "pinned host buffers in and out, forward half: mv, flags and the int8 indices in packed form "
-                            "(per-8x8 bitmap + non-zero values, exact) come back",
+                     "e2e": "pinned host buffers in and out, forward half: mv, flags and the int8 indices come back, dense or in "
+                            "packed form (per-8x8 bitmap + non-zero values, exact): both calls are timed, the faster one is "
+                            "the headline (e2e.variant)",
                      "cpu": "forward half: mv, cost, flags, int8 indices (what e2e returns), preallocated outputs"},
             "H": H, "W": W, "frames_per_clip": T, "clips_per_step": "one per GPU", "block": BS, "range": R,
             "gop": GOP, "qf": QF, "metric": "wrap8", "static_thr": STATIC_THR,
@@ -353,29 +354,47 @@ def run_b200(args, rank, world, local_rank):
         static_frac = float((dout["flags"] & 1).float().mean().item())
 
         # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------
-        # the int8 indices come back PACKED (per-block bitmap + non-zero values, exact); winning costs stay on the device
-        hout = ce.alloc_host_packed(T, want_recon=False, pinned=True)
-        for _ in range(max(1, args.warmup)):
-            ce.encode_host_packed(host_in, hout)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            ce.encode_host_packed(host_in, hout)
-        torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        if dist is not None:
-            dist.barrier()
+        # Two public calls return the same information: vcs_encode_clip_host (dense int8 planes) and
+        # vcs_encode_clip_host_packed (per-block bitmap + non-zero values, exact).  Both are timed; the headline is
+        # the faster one at this N (dense while one GPU owns the PCIe link, packed once the ranks share the fabric).
         from vcs_h264_b200 import container
+
+        def time_e2e(run):
+            for _ in range(max(1, args.warmup)):
+                run()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                run()
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            if dist is not None:
+                dist.barrier()
+            return dt
+        hden = ce.alloc_host_outputs(T, want_coef=True, want_recon=False, pinned=True)
+        del hden["cost"]                                  # the winning costs stay on the device unless asked for
+        dt_dense = time_e2e(lambda: ce.encode_host(host_in, hden))
+        same_dense = bool(torch.equal(hden["mv"], dout["mv"].cpu()) and torch.equal(hden["coef"], dout["coef"].cpu()))
+        d2h_dense = sum(hden[k].numel() * hden[k].element_size() for k in ("mv", "flags", "coef"))
+        del hden
+        hout = ce.alloc_host_packed(T, want_recon=False, pinned=True)
+        dt_packed = time_e2e(lambda: ce.encode_host_packed(host_in, hout))
         dense = container.expand_packed(hout["bitmap"].numpy(), hout["row_count"].numpy(),
                                         hout["values"].numpy()[:hout["nvalues"]], H, W)
-        same = bool(torch.equal(hout["mv"], dout["mv"].cpu()) and torch.equal(torch.from_numpy(dense), dout["coef"].cpu()))
+        same_packed = bool(torch.equal(hout["mv"], dout["mv"].cpu()) and torch.equal(torch.from_numpy(dense), dout["coef"].cpu()))
         del dense
+        d2h_packed = sum(hout[k].numel() * hout[k].element_size() for k in ("mv", "flags", "bitmap", "row_count")) + hout["nvalues"]
         h2d = host_in.numel()
-        d2h = sum(hout[k].numel() * hout[k].element_size() for k in ("mv", "flags", "bitmap", "row_count")) + hout["nvalues"]
+        variants = {"dense": {"call": "vcs_encode_clip_host", "frames_per_s": world * T * args.steps / dt_dense,
+                              "ms_per_step": 1e3 * dt_dense / args.steps, "d2h_bytes_per_step": d2h_dense, "host_equals_device": same_dense},
+                    "packed": {"call": "vcs_encode_clip_host_packed", "frames_per_s": world * T * args.steps / dt_packed,
+                               "ms_per_step": 1e3 * dt_packed / args.steps, "d2h_bytes_per_step": d2h_packed, "host_equals_device": same_packed}}
+        best = "packed" if dt_packed <= dt_dense else "dense"
+        dt, d2h, same = (dt_packed, d2h_packed, same_packed) if best == "packed" else (dt_dense, d2h_dense, same_dense)
         got = {k: dout[k].cpu().numpy() for k in ("mv", "cost", "flags", "coef", "recon")} if metric == _capi.METRIC_WRAP8 and rank == 0 else None
         return dict(got=got, ms=ms, launches=launches, me_ms=me_ms / max(ncalls, 1), dct_ms=dct_ms / max(ncalls, 1),
                     e2e_fps=world * T * args.steps / dt, e2e_ms=1e3 * dt / args.steps, h2d=h2d, d2h=d2h,
-                    clocks=clocks, static_frac=static_frac, host_equals_device=same)
+                    clocks=clocks, static_frac=static_frac, host_equals_device=same, e2e_variant=best, e2e_variants=variants)
 
     ctx0 = v.runtime.get_context(local_rank)
     ctx0.set_stream(stream.cuda_stream)
@@ -534,7 +553,8 @@ def run_b200(args, rank, world, local_rank):
         "config": workload_config(), "clocks": wrap["clocks"],
         "e2e": {"value": wrap["e2e_fps"], "unit": "frames/s", "h2d_bytes_per_step": wrap["h2d"],
                 "d2h_bytes_per_step": wrap["d2h"], "ms_per_step": wrap["e2e_ms"],
-                "host_equals_device": wrap["host_equals_device"]},
+                "host_equals_device": wrap["host_equals_device"], "variant": wrap["e2e_variant"],
+                "variants": wrap["e2e_variants"]},
         "gpu_launches": wrap["launches"],
         "roofline": me_roof(wrap, 3), "roofline_dct": dct_roof(wrap),
         "static_fraction": wrap["static_frac"], "microbench": mb, "host_numa_cpus_rank0": numa,

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <vector>
 
@@ -915,6 +916,12 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
         CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->chunk_events.push_back(e);
     }
+    // VCS_TRACE=1: a timeline of the pipeline on stderr (timing-enabled events; diagnostics only)
+    const bool trace = getenv("VCS_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto tmark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+    const double host_t0 = trace ? (double)clock() / CLOCKS_PER_SEC : 0.0;
+    if (trace) { cudaStreamSynchronize(ctx->stream); tmark(ctx->stream); cudaStreamWaitEvent(ctx->s_h2d, tev[0], 0); cudaStreamWaitEvent(ctx->s_d2h, tev[0], 0); }
     // (Running consecutive searches on two streams so that one fills the other's tail was tried and is slower:
     // the persistent search CTAs of the next chunk then keep the DCT stage of this chunk off the SMs.)
     cudaStream_t sc = ctx->stream;
@@ -949,6 +956,8 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
             CK(ctx, cudaStreamWaitEvent(sc, ctx->chunk_events[2 * c], 0));
             uploaded = t_need;
         }
+        tmark(ctx->s_h2d);   // 1 + 4c: upload of segment c done
+        tmark(sc);           // 2 + 4c: compute of segment c may start (previous compute done)
         {
             const int g0 = p0 / ppg;
             FrameAddr fa = clip_addr(d_fr + fs * (size_t)g0 * gop_len, p->H, p->W, gop_len);
@@ -966,6 +975,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
                 return rc;
         }
         CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sc));
+        tmark(sc);           // 3 + 4c: compute of segment c done
         if (pk) {
             CK(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->chunk_events[2 * c + 1], 0));
             CK(ctx, cudaMemcpyAsync(&ctx->h_segend[c], d_total + 1 + c, 8, cudaMemcpyDeviceToHost, ctx->s_aux));
@@ -973,6 +983,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
         } else {
             CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->chunk_events[2 * c + 1], 0));
             if (np > 0 && (rc = download(p0, np))) return rc;
+            tmark(ctx->s_d2h);   // 4 + 4c: download of segment c done (dense sink)
         }
         p0 += np;
     }
@@ -994,6 +1005,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
                                     (size_t)np * rows_per_p * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
             if ((rc = download(p0, np))) return rc;
         }
+        tmark(ctx->s_d2h);       // 4 + 4c (packed sink: appended after the pass-1 marks): download of segment c done
         host_values = end;
         *pk->nvalues = host_values;
         p0 += np;
@@ -1004,6 +1016,18 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
     // success or not, nothing may still be reading or writing the caller's buffers when this returns
     cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(sc), e3 = cudaStreamSynchronize(ctx->s_d2h),
                 e4 = cudaStreamSynchronize(ctx->s_aux);
+    if (trace && !tev.empty()) {
+        auto ms = [&](size_t k) { float t = 0; cudaEventElapsedTime(&t, tev[0], tev[k]); return t; };
+        fprintf(stderr, "[vcs trace] %d segments, %s sink; per segment: P-frames | upload done, compute start, compute done, download done (ms)\n",
+                nsegs, pk ? "packed" : "dense");
+        for (int c = 0; c < nsegs; ++c) {
+            const size_t b = 1 + (size_t)(pk ? 3 : 4) * c;
+            const size_t dl = pk ? 1 + 3 * (size_t)nsegs + c : b + 3;
+            if (dl < tev.size())
+                fprintf(stderr, "[vcs trace] seg %2d np %2d | %7.3f %7.3f %7.3f %7.3f\n", c, sizes[c], ms(b), ms(b + 1), ms(b + 2), ms(dl));
+        }
+        for (auto e : tev) cudaEventDestroy(e);
+    }
     if (rc) return rc;
     CK(ctx, e1); CK(ctx, e2); CK(ctx, e3); CK(ctx, e4);
     return pending_device_error(ctx);

@@ -205,7 +205,7 @@ def workload_config():
                         "8x8 DCT f64, quant QF50 -> int8 indices (lossless: |idx| <= 1024/min(Q) = 102)",
             "legs": {"value": "device-resident, forward + dequant, IDCT, reconstruction (outputs stay in HBM)",
                      "e2e": "pinned host buffers in and out, forward half: mv, flags and the int8 indices come back, dense or in "
-                            "packed form (per-8x8 bitmap + non-zero values, exact): both calls are timed, the faster one is "
+                            "packed form (per-8x8 bitmap + 4-bit codes + escapes, exact): both calls are timed, the faster one is "
                             "the headline (e2e.variant)",
                      "cpu": "forward half: mv, cost, flags, int8 indices (what e2e returns), preallocated outputs"},
             "H": H, "W": W, "frames_per_clip": T, "clips_per_step": "one per GPU", "block": BS, "range": R,
@@ -355,7 +355,7 @@ def run_b200(args, rank, world, local_rank):
 
         # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------
         # Two public calls return the same information: vcs_encode_clip_host (dense int8 planes) and
-        # vcs_encode_clip_host_packed (per-block bitmap + non-zero values, exact).  Both are timed; the headline is
+        # vcs_encode_clip_host_packed (per-block bitmap + 4-bit codes + escapes, exact).  Both are timed; the headline is
         # the faster one at this N (dense while one GPU owns the PCIe link, packed once the ranks share the fabric).
         from vcs_h264_b200 import container
 
@@ -380,10 +380,10 @@ def run_b200(args, rank, world, local_rank):
         hout = ce.alloc_host_packed(T, want_recon=False, pinned=True)
         dt_packed = time_e2e(lambda: ce.encode_host_packed(host_in, hout))
         dense = container.expand_packed(hout["bitmap"].numpy(), hout["row_count"].numpy(),
-                                        hout["values"].numpy()[:hout["nvalues"]], H, W)
+                                        hout["nibbles"].numpy()[:hout["lengths"][0]], hout["escapes"].numpy()[:hout["lengths"][1]], H, W)
         same_packed = bool(torch.equal(hout["mv"], dout["mv"].cpu()) and torch.equal(torch.from_numpy(dense), dout["coef"].cpu()))
         del dense
-        d2h_packed = sum(hout[k].numel() * hout[k].element_size() for k in ("mv", "flags", "bitmap", "row_count")) + hout["nvalues"]
+        d2h_packed = ce.packed_bytes(hout)
         h2d = host_in.numel()
         variants = {"dense": {"call": "vcs_encode_clip_host", "frames_per_s": world * T * args.steps / dt_dense,
                               "ms_per_step": 1e3 * dt_dense / args.steps, "d2h_bytes_per_step": d2h_dense, "host_equals_device": same_dense},
@@ -488,7 +488,8 @@ def run_b200(args, rank, world, local_rank):
             ce.encode_host_packed(host_in3, hout)
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - tw) / steps
-        same = bool(torch.equal(hout["mv"], dout["mv"].cpu()) and hout["nvalues"] == int((dout["coef"] != 0).sum().item()))
+        c8 = dout["coef"]
+        same = bool(torch.equal(hout["mv"], dout["mv"].cpu()) and hout["lengths"][1] == int(((c8 < -8) | (c8 > 7)).sum().item()))
         res = {"workload": "C3: one synthetic 2160x3840 240-frame clip (60 GOPs, I-P-P-P), 16x16 MB, +/-32 step-1 full search, "
                            "reference cost + static test, residual, 8x8 DCT f64, quant QF50 -> int8 indices; GOP-sharded "
                            "(sharding.frame_range), per-shard vectors/flags/indices all_gathered over NCCL every step",
@@ -498,7 +499,7 @@ def run_b200(args, rank, world, local_rank):
                "gpu_launches": launches,
                "gathered_bytes_per_step_per_rank": plan.bytes_per_step() if plan is not None else 0,
                "e2e": {"value": T3 / dt, "unit": "frames/s", "ms_per_step": dt * 1e3, "h2d_bytes_per_step": int(host_in3.numel()),
-                       "d2h_bytes_per_step": int(sum(hout[k].numel() * hout[k].element_size() for k in ("mv", "flags", "bitmap", "row_count")) + hout["nvalues"]),
+                       "d2h_bytes_per_step": int(ce.packed_bytes(hout)),
                        "host_equals_device": same},
                "check": check}
         del shard, dout, host_in3, hout, base

@@ -180,29 +180,38 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
 
 /*
  * Packed form of the int8 indices (the wire form of Frame.r, frame.py:1-8; the reference keeps dense float64 planes
- * and never wrote the zero-run stage its proposal promised).  Per 8x8 block a 64-bit occupancy bitmap (bit 8*i+j =
- * row i, column j of the block) and, in ONE byte stream for the clip, the block's non-zero values in bit order;
- * blocks in (P-frame, channel Y/Cr/Cb, block row, block column) order; row_count[p][ch][by] = number of values of a
- * block row, so rows can be located by a prefix sum.  Exact (lossless) whenever int8 indices are (QF <= 50).
+ * and never wrote the zero-run stage its proposal promised).  Exact (lossless) whenever int8 indices are (QF <= 50):
+ *   bitmap    uint64 [nP][3][H/8][W/8]  occupancy of every 8x8 block, bit 8*i+j = row i, column j
+ *   nibbles   uint8 stream: one 4-bit code per non-zero index of a block in bit order, low nibble first, every block
+ *             padded to a whole byte; code = v & 15 for v in [-8, 7], code 0 = escape
+ *   escapes   int8 stream: the value of every escaped index, in the same order
+ *   row_count uint32 [nP][3][H/8][2]    per block row: bytes of its nibble stream, number of its escapes (a prefix
+ *             sum locates any block row in both streams)
+ * Blocks in (P-frame, channel Y/Cr/Cb, block row, block column) order; both streams run through the whole clip.
  *
- * vcs_encode_clip_host_packed = vcs_encode_clip_host with VCS_COEF_I8_RINT whose coefficients come back packed:
- * bitmap uint64 [nP][3][H/8][W/8], row_count uint32 [nP][3][H/8], values int8 (values_capacity bytes; 3*H*W*nP is
- * always enough), *nvalues = bytes written.  The dense planes never cross the bus.
+ * vcs_encode_clip_host_packed = vcs_encode_clip_host with VCS_COEF_I8_RINT whose coefficients come back packed; the
+ * dense planes never cross the bus.  nibbles_capacity = 3*H*W*nP/2 + 3*(H/8)*(W/8)*nP and escapes_capacity =
+ * 3*H*W*nP are always enough; smaller buffers are refused with VCS_E_INVALID when they overflow.  lengths[2] (out) =
+ * bytes of the nibble stream, number of escapes.
  */
 int vcs_encode_clip_host_packed(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
                                 int16_t *mv, uint32_t *cost, uint8_t *flags, uint64_t *bitmap, uint32_t *row_count,
-                                int8_t *values, size_t values_capacity, uint64_t *nvalues, uint8_t *recon);
-/* dense int8 planes [nP][3][H][W] -> packed (all DEVICE pointers; *nvalues_host is a host pointer; synchronises) */
+                                uint8_t *nibbles, size_t nibbles_capacity, int8_t *escapes, size_t escapes_capacity,
+                                uint64_t *lengths, uint8_t *recon);
+/* dense int8 planes [nP][3][H][W] -> packed (all DEVICE pointers, worst-case capacities as above; lengths_host[2] is
+ * a host pointer; synchronises) */
 int vcs_pack_coef_dev(vcs_ctx *ctx, int H, int W, int nP, const int8_t *coef, uint64_t *bitmap, uint32_t *row_count,
-                      int8_t *values, uint64_t *nvalues_host);
-/* the exact inverse (all DEVICE pointers, enqueued on the context's stream); a stream shorter than its bitmaps claim
- * is never read past its end: the affected blocks decode to zero and the context reports VCS_E_INVALID */
+                      uint8_t *nibbles, int8_t *escapes, uint64_t *lengths_host);
+/* the exact inverse (all DEVICE pointers, enqueued on the context's stream); streams shorter than their bitmaps claim
+ * are never read past their end: the affected blocks decode to zero and the context reports VCS_E_INVALID */
 int vcs_unpack_coef_dev(vcs_ctx *ctx, int H, int W, int nP, const uint64_t *bitmap, const uint32_t *row_count,
-                        const int8_t *values, uint64_t nvalues, int8_t *coef);
+                        const uint8_t *nibbles, uint64_t nnibble_bytes, const int8_t *escapes, uint64_t nescapes,
+                        int8_t *coef);
 /* vcs_decode_clip_host from the packed form (host buffers) */
 int vcs_decode_clip_host_packed(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_frames, int T, int gop_len,
                                 const int16_t *mv, const uint64_t *bitmap, const uint32_t *row_count,
-                                const int8_t *values, uint64_t nvalues, uint8_t *recon);
+                                const uint8_t *nibbles, uint64_t nnibble_bytes, const int8_t *escapes, uint64_t nescapes,
+                                uint8_t *recon);
 
 /* ---- decoder side: Decoder._reconstruct_P_frame over a clip (decoder.py:52-69) --------------------- */
 /* ref_frames: the ORIGINAL I-frames only, uint8 [nG][H][W][3] (Decoder.ref_frames); mv / coef indexed by

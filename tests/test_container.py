@@ -99,26 +99,40 @@ def test_container_feeds_both_decoders():
 
 
 def test_packed_form_round_trip():
-    """Version-2 container: bitmap + row counts + value stream is an exact re-coding of the dense int8 indices."""
+    """Version-2 container: bitmap + 4-bit codes + escapes is an exact re-coding of the dense int8 indices."""
     rng = np.random.default_rng(7)
     c = _random_clip(rng, T=5, H=40, W=72, bs=8, gop=3, cm=_capi.COEF_I8_RINT)
     coef = c["coef"].copy()
+    small = rng.integers(-8, 8, coef.shape).astype(np.int8)
+    pick = rng.random(coef.shape) < 0.8                    # most indices are small, like on real residuals
+    coef[pick] = small[pick]
     coef[rng.random(coef.shape) < 0.6] = 0                 # the bench clip is 57 % zeros
     coef[0, 0, :8, :8] = 0                                 # an empty block
     coef[1, 2, 8:16, 16:24] = 5                            # a full one
-    bitmap, row_count, values = container.compact_dense(coef)
-    assert bitmap.dtype == np.uint64 and bitmap.shape == (3, 3, 5, 9) and row_count.shape == (3, 3, 5)
-    assert values.size == np.count_nonzero(coef) == int(row_count.sum())
+    coef[2, 1, :8, :8] = -8                                # the edges of the code range ...
+    coef[2, 1, 8:16, :8] = 7
+    coef[2, 1, 16:24, :8] = -9                             # ... and the first escapes on either side
+    coef[2, 1, 24:32, :8] = 8
+    coef[2, 0, 0, :3] = [-128, 127, 1]                     # an odd number of values in a block: padded to a byte
+    bitmap, row_count, nibbles, escapes = container.compact_dense(coef)
+    assert bitmap.dtype == np.uint64 and bitmap.shape == (3, 3, 5, 9) and row_count.shape == (3, 3, 5, 2)
+    nz = coef != 0
+    assert escapes.size == np.count_nonzero(nz & ((coef < -8) | (coef > 7))) == int(row_count[..., 1].sum())
+    assert nibbles.size == int(row_count[..., 0].sum())
     assert bitmap[0, 0, 0, 0] == 0 and bitmap[1, 2, 1, 2] == np.uint64(2 ** 64 - 1)
-    assert np.array_equal(container.expand_packed(bitmap, row_count, values, 40, 72), coef)
-    blob = container.pack_packed(c["i_frames"], c["mv"], bitmap, row_count, values, T=5, block_size=8, gop_len=3)
-    assert len(blob) == 64 + 1536 + c["i_frames"].size + c["mv"].size * 2 + bitmap.size * 8 + row_count.size * 4 + values.size
+    assert np.array_equal(container.expand_packed(bitmap, row_count, nibbles, escapes, 40, 72), coef)
+    blob = container.pack_packed(c["i_frames"], c["mv"], bitmap, row_count, nibbles, escapes, T=5, block_size=8, gop_len=3)
+    assert len(blob) == (64 + 1536 + c["i_frames"].size + c["mv"].size * 2 + bitmap.size * 8 + row_count.size * 4
+                         + nibbles.size + escapes.size)
     u = container.unpack(blob)
-    assert u["version"] == 2 and u["nvalues"] == values.size
-    assert np.array_equal(u["bitmap"], bitmap) and np.array_equal(u["row_count"], row_count) and np.array_equal(u["values"], values)
+    assert u["version"] == 2 and u["lengths"] == (nibbles.size, escapes.size)
+    for k, want in (("bitmap", bitmap), ("row_count", row_count), ("nibbles", nibbles), ("escapes", escapes)):
+        assert np.array_equal(u[k], want), k
     frames, refs = container.to_frames(u)
     assert np.array_equal(frames[1].r[0], coef[0, 0].astype(np.float64)) and frames[1].r[0].dtype == np.float64
     with pytest.raises(ValueError):
         container.unpack(blob[:-1])
     with pytest.raises(ValueError):
-        container.expand_packed(bitmap, row_count, values[:-1], 40, 72)
+        container.expand_packed(bitmap, row_count, nibbles[:-1], escapes, 40, 72)
+    with pytest.raises(ValueError):
+        container.expand_packed(bitmap, row_count, nibbles, escapes[:-1], 40, 72)

@@ -9,6 +9,21 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+def _planes(rng, nP, H, W):
+    coef = rng.integers(-128, 128, (nP, 3, H, W)).astype(np.int8)
+    small = rng.integers(-8, 8, coef.shape).astype(np.int8)
+    pick = rng.random(coef.shape) < 0.85
+    coef[pick] = small[pick]
+    coef[rng.random(coef.shape) < 0.57] = 0
+    coef[0, 0, :8, :8] = 0
+    coef[-1, 2, -8:, -8:] = -3
+    coef[-1, 1, -8:, :8] = 99                              # a block of 64 escapes
+    coef[0, 1, 0, :5] = [-8, 7, -9, 8, 1]
+    if nP > 1:
+        coef[1] = 0                                        # a whole frame of empty blocks
+    return coef
+
+
 @pytest.mark.parametrize("geom", [(1, 8, 8), (2, 40, 72), (3, 64, 8 * 33), (2, 536, 960)])
 def test_pack_unpack_device_round_trip(geom):
     import torch
@@ -16,62 +31,81 @@ def test_pack_unpack_device_round_trip(geom):
     from vcs_h264_b200 import _capi, container
     nP, H, W = geom
     ctx = _capi.Context(0)
-    rng = np.random.default_rng(H * W)
-    coef = rng.integers(-100, 101, (nP, 3, H, W)).astype(np.int8)
-    coef[rng.random(coef.shape) < 0.57] = 0
-    coef[0, 0, :8, :8] = 0
-    coef[-1, 2, -8:, -8:] = -3
-    if nP > 1:
-        coef[1] = 0                                        # a whole frame of empty blocks
+    coef = _planes(np.random.default_rng(H * W), nP, H, W)
     d = torch.from_numpy(coef).cuda()
     bitmap = torch.empty((nP, 3, H // 8, W // 8), dtype=torch.int64, device="cuda")
-    row_count = torch.empty((nP, 3, H // 8), dtype=torch.int32, device="cuda")
-    values = torch.full((coef.size + 64,), 77, dtype=torch.int8, device="cuda")
-    n = C.c_uint64(0)
-    ctx.call("vcs_pack_coef_dev", H, W, nP, d.data_ptr(), bitmap.data_ptr(), row_count.data_ptr(), values.data_ptr(), C.byref(n))
-    wb, wr, wv = container.compact_dense(coef)
-    assert n.value == wv.size == np.count_nonzero(coef)
+    row_count = torch.empty((nP, 3, H // 8, 2), dtype=torch.int32, device="cuda")
+    nibbles = torch.full((coef.size // 2 + bitmap.numel() + 64,), 77, dtype=torch.uint8, device="cuda")
+    escapes = torch.full((coef.size + 64,), 77, dtype=torch.int8, device="cuda")
+    n = (C.c_uint64 * 2)(0, 0)
+    ctx.call("vcs_pack_coef_dev", H, W, nP, d.data_ptr(), bitmap.data_ptr(), row_count.data_ptr(), nibbles.data_ptr(),
+             escapes.data_ptr(), n)
+    wb, wr, wn, we = container.compact_dense(coef)
+    assert (n[0], n[1]) == (wn.size, we.size)
     assert np.array_equal(bitmap.cpu().numpy().view(np.uint64), wb)
     assert np.array_equal(row_count.cpu().numpy().view(np.uint32), wr)
-    assert np.array_equal(values[:n.value].cpu().numpy(), wv)
-    assert bool((values[n.value:] == 77).all())            # nothing written past the stream
+    assert np.array_equal(nibbles[:n[0]].cpu().numpy(), wn)
+    assert np.array_equal(escapes[:n[1]].cpu().numpy(), we)
+    assert bool((nibbles[n[0]:] == 77).all()) and bool((escapes[n[1]:] == 77).all())      # nothing written past the streams
     back = torch.full_like(d, 55)
-    ctx.call("vcs_unpack_coef_dev", H, W, nP, bitmap.data_ptr(), row_count.data_ptr(), values.data_ptr(), n.value, back.data_ptr())
+    ctx.call("vcs_unpack_coef_dev", H, W, nP, bitmap.data_ptr(), row_count.data_ptr(), nibbles.data_ptr(), n[0],
+             escapes.data_ptr(), n[1], back.data_ptr())
     ctx.synchronize()
     assert torch.equal(back, d)
-    if n.value > 10:                                       # a truncated stream is refused, not read past its end
-        ctx.call("vcs_unpack_coef_dev", H, W, nP, bitmap.data_ptr(), row_count.data_ptr(), values.data_ptr(), n.value - 10, back.data_ptr())
+    if n[0] > 10:                                          # truncated streams are refused, not read past their end
+        ctx.call("vcs_unpack_coef_dev", H, W, nP, bitmap.data_ptr(), row_count.data_ptr(), nibbles.data_ptr(), n[0] - 10,
+                 escapes.data_ptr(), n[1], back.data_ptr())
+        with pytest.raises(v.VcsError):
+            ctx.synchronize()
+    if n[1] > 3:
+        ctx.call("vcs_unpack_coef_dev", H, W, nP, bitmap.data_ptr(), row_count.data_ptr(), nibbles.data_ptr(), n[0],
+                 escapes.data_ptr(), n[1] - 3, back.data_ptr())
         with pytest.raises(v.VcsError):
             ctx.synchronize()
     ctx.close()
 
 
-@pytest.mark.parametrize("T,H,W,bs,R", [(13, 96, 160, 16, 16), (60, 1080 // 4 // 8 * 8, 1920 // 4, 16, 16), (5, 72, 104, 8, 8)])
-def test_clip_packed_equals_dense(T, H, W, bs, R):
+@pytest.mark.parametrize("T,H,W,bs,R,qf", [(13, 96, 160, 16, 16, 50.0), (60, 1080 // 4 // 8 * 8, 1920 // 4, 16, 16, 50.0),
+                                            (5, 72, 104, 8, 8, 50.0), (9, 64, 96, 16, 8, 20.0)])
+def test_clip_packed_equals_dense(T, H, W, bs, R, qf):
     """The pipelined host path with the packed sink returns the same vectors and, expanded, the same indices as the dense
     path; both decoders reconstruct the same frames from it."""
     import vcs_h264_b200 as v
     from vcs_h264_b200 import container, synth
     clip = synth.clip(T, H, W, seed=T * 7 + H, margin=64)
-    ce = v.ClipEncoder([H, W], block_size=bs, search="full", search_range=R, gop_len=4, qf=50.0, coef_mode=v.COEF_I8_RINT)
+    ce = v.ClipEncoder([H, W], block_size=bs, search="full", search_range=R, gop_len=4, qf=qf, coef_mode=v.COEF_I8_RINT)
     dense = ce.encode_host(clip, want_coef=True, want_recon=True)
-    pk = ce.encode_host_packed(clip, want_recon=True)
-    coef = np.asarray(dense["coef"])
-    assert np.array_equal(np.asarray(pk["mv"]), np.asarray(dense["mv"]))
-    assert np.array_equal(np.asarray(pk["flags"]), np.asarray(dense["flags"]))
-    assert np.array_equal(np.asarray(pk["recon"]), np.asarray(dense["recon"]))
-    assert pk["nvalues"] == np.count_nonzero(coef)
-    vals = np.asarray(pk["values"])[:pk["nvalues"]]
-    assert np.array_equal(container.expand_packed(np.asarray(pk["bitmap"]), np.asarray(pk["row_count"]), vals, H, W), coef)
-    cd = v.ClipDecoder([H, W], block_size=bs, gop_len=4, qf=50.0, coef_mode=v.COEF_I8_RINT)
-    rec = cd.decode_host_packed(clip[::4], pk["mv"], pk["bitmap"], pk["row_count"], pk["values"], pk["nvalues"], T)
+    for want_recon in (False, True):          # forward-only: the DCT stage emits bitmaps and counts; with recon: count kernel
+        pk = ce.encode_host_packed(clip, want_recon=want_recon)
+        coef = np.asarray(dense["coef"])
+        assert np.array_equal(np.asarray(pk["mv"]), np.asarray(dense["mv"]))
+        assert np.array_equal(np.asarray(pk["flags"]), np.asarray(dense["flags"]))
+        if want_recon:
+            assert np.array_equal(np.asarray(pk["recon"]), np.asarray(dense["recon"]))
+        wb, wr, wn, we = container.compact_dense(coef)
+        assert pk["lengths"] == (wn.size, we.size)
+        assert np.array_equal(np.asarray(pk["bitmap"]).view(np.uint64), wb)
+        assert np.array_equal(np.asarray(pk["row_count"]).view(np.uint32), wr)
+        assert np.array_equal(np.asarray(pk["nibbles"])[:wn.size], wn)
+        assert np.array_equal(np.asarray(pk["escapes"])[:we.size], we)
+    cd = v.ClipDecoder([H, W], block_size=bs, gop_len=4, qf=qf, coef_mode=v.COEF_I8_RINT)
+    rec = cd.decode_host_packed(clip[::4], pk["mv"], pk["bitmap"], pk["row_count"], pk["nibbles"], pk["escapes"], pk["lengths"], T)
     assert np.array_equal(rec, np.asarray(dense["recon"]))
     # through the version-2 container
-    blob = container.pack_packed(clip[::4], pk["mv"], pk["bitmap"], pk["row_count"], pk["values"], pk["nvalues"],
-                                 T=T, block_size=bs, gop_len=4)
+    blob = container.pack_packed(clip[::4], pk["mv"], pk["bitmap"], pk["row_count"], pk["nibbles"], pk["escapes"], pk["lengths"],
+                                 T=T, block_size=bs, gop_len=4, qf=qf)
     u = container.unpack(blob)
-    rec2 = cd.decode_host_packed(u["i_frames"], u["mv"], u["bitmap"], u["row_count"], u["values"], u["nvalues"], T)
+    rec2 = cd.decode_host_packed(u["i_frames"], u["mv"], u["bitmap"], u["row_count"], u["nibbles"], u["escapes"], u["lengths"], T)
     assert np.array_equal(rec2, rec)
-    dense_bytes = coef.size
-    packed_bytes = np.asarray(pk["bitmap"]).nbytes + np.asarray(pk["row_count"]).nbytes + pk["nvalues"]
-    assert packed_bytes < dense_bytes
+    assert v.ClipEncoder.packed_bytes(pk) < coef.size
+
+
+def test_small_escape_buffer_is_refused():
+    import vcs_h264_b200 as v
+    from vcs_h264_b200 import synth
+    T, H, W = 5, 64, 96
+    clip = synth.clip(T, H, W, seed=3, margin=48)
+    ce = v.ClipEncoder([H, W], block_size=16, search="full", search_range=8, gop_len=4, qf=50.0, coef_mode=v.COEF_I8_RINT)
+    out = ce.alloc_host_packed(T, pinned=False, escape_fraction=0.0)       # 64 bytes only
+    with pytest.raises(v.VcsError, match="too small"):
+        ce.encode_host_packed(clip, out)

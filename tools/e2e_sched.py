@@ -32,6 +32,6 @@ for s in scheds:
         run()
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) / n * 1e3
-    sig = (int(hout["mv"].to(torch.int64).sum()), int(hout["coef"].to(torch.int64).abs().sum()) if dense else (hout["nvalues"], int(hout["values"][:hout["nvalues"]].to(torch.int64).abs().sum())))
+    sig = (int(hout["mv"].to(torch.int64).sum()), int(hout["coef"].to(torch.int64).abs().sum()) if dense else (hout["lengths"], int(hout["nibbles"][:hout["lengths"][0]].to(torch.int64).sum())))
     ref = ref or sig
     print(f"sched {s or 'default':24s} {ms:7.3f} ms  {bench.T / ms * 1e3:7.1f} fps  same={sig == ref}", flush=True)

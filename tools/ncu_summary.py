@@ -20,10 +20,25 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
 STALL = "smsp__average_warps_issue_stalled_"
 
 
+SCALE = {"ns": ("ms", 1e-6), "us": ("ms", 1e-3), "ms": ("ms", 1.0), "s": ("ms", 1e3), "nsecond": ("ms", 1e-6), "usecond": ("ms", 1e-3),
+         "msecond": ("ms", 1.0), "second": ("ms", 1e3), "byte": ("Mbyte", 1e-6), "Kbyte": ("Mbyte", 1e-3), "Mbyte": ("Mbyte", 1.0),
+         "Gbyte": ("Mbyte", 1e3)}
+
+
 def load(path):
+    """One capture as {metric: (unit, value)}; durations are normalised to ms and byte counts to Mbyte (ncu picks the
+    unit per capture)."""
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    return {k: (u, v) for k, u, v in zip(rows[0], rows[1], rows[2])}
+    d = {}
+    for k, u, v in zip(rows[0], rows[1], rows[2]):
+        if (k.startswith("gpu__time_duration") or k.startswith("dram__bytes")) and u in SCALE:
+            try:
+                u, v = SCALE[u][0], "%.6f" % (float(v.replace(",", "")) * SCALE[u][1])
+            except ValueError:
+                pass
+        d[k] = (u, v)
+    return d
 
 
 def main():

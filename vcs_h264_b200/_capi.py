@@ -77,10 +77,11 @@ SIGNATURES = {
     "vcs_residual_dct_clip_dev": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "vcs_encode_clip_dev": (_i, [_vp, _PP, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "vcs_encode_clip_host": (_i, [_vp, _PP, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "vcs_encode_clip_host_packed": (_i, [_vp, _PP, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, C.POINTER(C.c_uint64), _vp]),
-    "vcs_pack_coef_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(C.c_uint64)]),
-    "vcs_unpack_coef_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, C.c_uint64, _vp]),
-    "vcs_decode_clip_host_packed": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
+    "vcs_encode_clip_host_packed": (_i, [_vp, _PP, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz,
+                                         C.POINTER(C.c_uint64), _vp]),
+    "vcs_pack_coef_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_uint64)]),
+    "vcs_unpack_coef_dev": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp]),
+    "vcs_decode_clip_host_packed": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp]),
     "vcs_decode_clip_dev": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "vcs_decode_clip_host": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "vcs_count_nonzero_dev": (_i, [_vp, _i, _vp, _sz, C.POINTER(C.c_ulonglong)]),

@@ -95,39 +95,52 @@ class ClipEncoder:
                       _capi.ptr(out.get("recon")))
         return out
 
-    # -- host buffers in, PACKED coefficients out (bitmap + non-zero values: about half the dense int8 bytes) -----
-    def alloc_host_packed(self, T, want_recon=False, pinned=True):
+    # -- host buffers in, PACKED coefficients out (bitmap + 4-bit codes + escapes: about 40 % of the dense int8 bytes) ---
+    def alloc_host_packed(self, T, want_recon=False, pinned=True, escape_fraction=0.25):
+        """Output buffers of encode_host_packed.  The nibble stream gets its worst-case size; the escape stream
+        `escape_fraction` of its worst case (every index outside [-8, 7]); 1.0 can never overflow."""
         import torch
         nP = self.num_p_frames(T)
 
         def buf(shape, dtype):
             t = torch.empty(shape, dtype=dtype)
             return t.pin_memory() if pinned and torch.cuda.is_available() else t
+        ncoef, nblk = nP * 3 * self.H * self.W, nP * 3 * (self.H // 8) * (self.W // 8)
         out = dict(mv=buf((nP, self.N, 2), torch.int16), flags=buf((nP, self.N), torch.uint8),
                    bitmap=buf((nP, 3, self.H // 8, self.W // 8), torch.int64),      # uint64 bit patterns
-                   row_count=buf((nP, 3, self.H // 8), torch.int32),
-                   values=buf((nP * 3 * self.H * self.W,), torch.int8))
+                   row_count=buf((nP, 3, self.H // 8, 2), torch.int32),
+                   nibbles=buf((ncoef // 2 + nblk,), torch.uint8),
+                   escapes=buf((max(64, int(ncoef * escape_fraction)),), torch.int8))
         if want_recon:
             out["recon"] = buf((nP, self.H, self.W, 3), torch.uint8)
         return out
 
     def encode_host_packed(self, frames, out=None, want_recon=False):
         """Like encode_host with int8 indices, but the indices come back packed (include/vcs_b200.h:
-        vcs_encode_clip_host_packed).  out["nvalues"] = length of the value stream in bytes."""
+        vcs_encode_clip_host_packed).  out["lengths"] = (bytes of the nibble stream, number of escapes)."""
         import ctypes as C
         T = int(frames.shape[0])
         if tuple(frames.shape[1:]) != (self.H, self.W, 3):
             raise ValueError(f"frames must be [T,{self.H},{self.W},3] uint8")
         if out is None:
-            out = self.alloc_host_packed(T, want_recon, pinned=False)
-        n = C.c_uint64(0)
-        cap = out["values"].numel() if hasattr(out["values"], "numel") else out["values"].size
+            out = self.alloc_host_packed(T, want_recon, pinned=False, escape_fraction=1.0)
+        n = (C.c_uint64 * 2)(0, 0)
+
+        def size(a):
+            return a.numel() if hasattr(a, "numel") else a.size
         self.ctx.call("vcs_encode_clip_host_packed", self.params, _capi.ptr(frames), T, self.gop_len,
                       _capi.ptr(out["mv"]), _capi.ptr(out.get("cost")), _capi.ptr(out.get("flags")),
-                      _capi.ptr(out["bitmap"]), _capi.ptr(out["row_count"]), _capi.ptr(out["values"]), cap,
-                      C.byref(n), _capi.ptr(out.get("recon")))
-        out["nvalues"] = int(n.value)
+                      _capi.ptr(out["bitmap"]), _capi.ptr(out["row_count"]), _capi.ptr(out["nibbles"]), size(out["nibbles"]),
+                      _capi.ptr(out["escapes"]), size(out["escapes"]), n, _capi.ptr(out.get("recon")))
+        out["lengths"] = (int(n[0]), int(n[1]))
         return out
+
+    @staticmethod
+    def packed_bytes(out):
+        """Bytes of a packed result that carry information (what travels: vectors, flags, bitmaps, counts, streams)."""
+        def nbytes(a):
+            return a.numel() * a.element_size() if hasattr(a, "numel") else a.nbytes
+        return sum(nbytes(out[k]) for k in ("mv", "flags", "bitmap", "row_count") if out.get(k) is not None) + sum(out["lengths"])
 
     # -- device resident (bench.py value) --------------------------------------------------------
     def alloc_device_outputs(self, T, want_coef=True, want_recon=True):
@@ -206,18 +219,19 @@ class ClipDecoder:
                       mv.ctypes.data, self.coef_mode, coef.ctypes.data, out.ctypes.data)
         return out
 
-    def decode_host_packed(self, ref_frames, mv, bitmap, row_count, values, nvalues, T):
-        """decode_host from the packed coefficient form (ClipEncoder.encode_host_packed / container v2)."""
+    def decode_host_packed(self, ref_frames, mv, bitmap, row_count, nibbles, escapes, lengths, T):
+        """decode_host from the packed coefficient form (ClipEncoder.encode_host_packed / container version 2)."""
         nP = _capi.num_p_frames(T, self.gop_len)
         mv = np.ascontiguousarray(np.asarray(mv), np.int16)
         ref_frames = np.ascontiguousarray(np.asarray(ref_frames), np.uint8)
         bitmap = np.ascontiguousarray(np.asarray(bitmap)).view(np.uint64)
         row_count = np.ascontiguousarray(np.asarray(row_count)).view(np.uint32)
-        values = np.ascontiguousarray(np.asarray(values)[:nvalues], np.int8)
+        nibbles = np.ascontiguousarray(np.asarray(nibbles).reshape(-1)[:lengths[0]]).view(np.uint8)
+        escapes = np.ascontiguousarray(np.asarray(escapes).reshape(-1)[:lengths[1]]).view(np.int8)
         out = np.empty((nP, self.H, self.W, 3), np.uint8)
         self.ctx.call("vcs_decode_clip_host_packed", self.H, self.W, self.bs, ref_frames.ctypes.data, T, self.gop_len,
-                      mv.ctypes.data, bitmap.ctypes.data, row_count.ctypes.data, values.ctypes.data, int(nvalues),
-                      out.ctypes.data)
+                      mv.ctypes.data, bitmap.ctypes.data, row_count.ctypes.data, nibbles.ctypes.data, int(lengths[0]),
+                      escapes.ctypes.data, int(lengths[1]), out.ctypes.data)
         return out
 
     def decode_device(self, ref_frames_dev, mv_dev, coef_dev, recon_dev, T, stream=None):

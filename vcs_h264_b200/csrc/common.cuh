@@ -64,6 +64,12 @@ __device__ __forceinline__ uint32_t nz_nibble(uint32_t x) {
     return (((nz >> 7) * 0x01020408u) >> 24) & 0xfu;                              // gather bits 0,8,16,24 -> 0..3
 }
 
+// bit k = byte k of x is outside [-8, 7] (an escape; zero bytes are inside)
+__device__ __forceinline__ uint32_t esc_nibble(uint32_t x) {
+    const uint32_t t = ((x & 0x7f7f7f7fu) + 0x08080808u) ^ (x & 0x80808080u);   // bytewise x + 8 (mod 256)
+    return nz_nibble(t & 0xf0f0f0f0u);
+}
+
 template <int METRIC>
 __device__ __forceinline__ uint32_t cost4_acc(uint32_t r, uint32_t c, uint32_t acc) {
     if (METRIC == 0) return wrap4_acc(r, c, acc);

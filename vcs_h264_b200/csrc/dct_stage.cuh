@@ -68,10 +68,12 @@ struct DctArgs {
     const uint8_t *pred_in;  // inverse-only: optional pred image to add (decoder.py:57)
     uint8_t *recon;          // [nP][H][W][3] or nullptr
     int *err;                // mapped host flag: set when a motion vector points outside the frame
-    // packed sink (pack.cuh), int8 mode only: per 8x8 block its occupancy bitmap (8 bytes, byte i = row i) and per
-    // block row the number of non-zero indices (accumulated with atomics: zero it before the launch); may be null
-    uint8_t *bitmap;         // [nP][3][H/8][W/8][8]
-    uint32_t *row_count;     // [nP][3][H/8]
+    // packed sink (pack.cuh), int8 forward-only variant: per 8x8 block its occupancy bitmap (8 bytes, byte i = row i)
+    // and escape count, per block row {bytes of its nibble stream, escapes} accumulated with one 64-bit atomic per
+    // tile (zero the counts before the launch); all three null when unused
+    uint8_t *bitmap;                  // [nP][3][H/8][W/8][8]
+    uint8_t *blk_esc;                 // [nP][3][H/8][W/8]
+    unsigned long long *row_count;    // [nP][3][H/8], low word = nibble bytes, high word = escapes
 };
 
 // 24 bytes (8 BGR pixels) starting at an arbitrary byte address, as 6 words
@@ -323,7 +325,8 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                         // occupancy of this lane's 8 indices = byte rp_i of the block's bitmap; 32 lanes = 32 consecutive bytes
                         const uint32_t m8 = nz_nibble(pk[0]) | (nz_nibble(pk[1]) << 4);
                         a.bitmap[(((size_t)p * 3 + ch) * (H / 8) + ty) * (size_t)(W / 8) * 8 + (size_t)(tx * 4 + rp_blk) * 8 + rp_i] = (uint8_t)m8;
-                        nnz_lane[c] = __popc(m8);
+                        // low half: non-zero indices, high half: those outside [-8, 7] (escapes of the nibble code)
+                        nnz_lane[c] = __popc(m8) | ((__popc(esc_nibble(pk[0])) + __popc(esc_nibble(pk[1]))) << 16);
                     }
                 }
             }
@@ -332,8 +335,14 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                 for (int c = 0; c < DCT_NCH; ++c) {
                     uint32_t n = nnz_lane[c];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-                    if (lane == 0 && n) atomicAdd(a.row_count + ((size_t)p * 3 + ch0 + c) * (H / 8) + ty, n);
+                    for (int o = 1; o < 8; o <<= 1) n += __shfl_xor_sync(0xffffffffu, n, o);     // the block's 8 rows
+                    const uint32_t esc = n >> 16;
+                    if (row_on && rp_i == 0)
+                        a.blk_esc[(((size_t)p * 3 + ch0 + c) * (H / 8) + ty) * (size_t)(W / 8) + tx * 4 + rp_blk] = (uint8_t)esc;
+                    unsigned long long t = (((n & 0xffffu) + 1) >> 1) | ((unsigned long long)esc << 32);   // nibble bytes | escapes
+#pragma unroll
+                    for (int o = 8; o < 32; o <<= 1) t += shfl_xor_u64(t, o);                    // the tile's 4 blocks
+                    if (lane == 0 && t) atomicAdd(a.row_count + ((size_t)p * 3 + ch0 + c) * (H / 8) + ty, t);
                 }
             }
         } else if (do_inverse && row_on) {

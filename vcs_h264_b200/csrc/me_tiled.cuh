@@ -200,10 +200,20 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
         if (n_units > 1) issue(1);
     }
 
-    // per-thread role in the search: (macroblock, dx index inside the chunk)
-    const int mb = tid / ND, dxw = tid - mb * ND;
+    // per-thread role in the search: (macroblock, dx index inside the chunk).  A quarter-warp that straddles two
+    // macroblocks breaks the 3*dx bank rotation of its LDS.128 (2-way conflict), so when ND = 32k + 1 warp m takes
+    // dx 0..31 of macroblock m (every LDS of the macroblock words is then a pure broadcast, and a static or
+    // out-of-frame macroblock idles whole warps) and the leftover dx = ND-1 of all macroblocks share the last warp(s).
+    constexpr bool WARP_PER_MB = ND == 33 && 32 * NMB + NMB <= C::THREADS;
+    int mb, dxw;
+    if (WARP_PER_MB) {
+        if (tid < 32 * NMB) { mb = tid >> 5; dxw = tid & 31; }
+        else { mb = tid - 32 * NMB; dxw = 32; }
+    } else {
+        mb = tid / ND; dxw = tid - mb * ND;
+    }
     const int mbx = mb % MX, mby = mb / MX;
-    const bool has_item = tid < C::ITEMS;
+    const bool has_item = WARP_PER_MB ? tid < 33 * NMB : tid < C::ITEMS;
 
     for (long long s = 0; s < n_units; ++s) {
         int p, tx, ty, cy, cx; bool first, last;

@@ -2,129 +2,159 @@
 // of the reference's Frame.r planes; the reference itself keeps dense float64 planes, frame.py:1-8, and has no
 // bitstream -- proposal section 5.1 promised a zero-run stage that was never written).
 //
-// The reference's wrapped residual (motion.py:39) leaves the indices dense (43 % non-zero at QF 50 on the bench clip),
-// so the format is the cheapest one that is still exact: per 8x8 block a 64-bit occupancy bitmap (bit 8*i+j = row i,
-// column j) followed -- in one byte stream for the whole clip -- by the non-zero int8 values of the block in bit order.
-// Blocks are ordered (P-frame, channel Y/Cr/Cb, block row, block column); `row_count[p][ch][by]` holds the number of
-// values of one block row (W/8 blocks), so any block row can be located by a prefix sum and decoded independently.
-//   dense : 3*H*W bytes per P-frame           packed : 3*H*W/8 (bitmaps) + nnz (values) + 12*H/8 (row counts)
+// The reference's wrapped residual (motion.py:39) leaves the indices dense (43 % non-zero at QF 50 on the bench clip,
+// 92 % of those inside [-8, 7]), so the format is a cheap exact one:
+//   bitmap    uint64 per 8x8 block: occupancy, bit 8*i+j = row i, column j
+//   nibbles   one 4-bit code per non-zero index of the block in bit order, low nibble first, each block padded to a
+//             whole byte: code = v & 15 for v in [-8, 7] (never 0 there), code 0 = escape
+//   escapes   the int8 value of every escaped index, in the same order
+//   row_count uint32[2] per block row (W/8 blocks): bytes of its nibble stream, number of its escapes -- a prefix sum
+//             locates any block row in both streams, so rows decode independently
+// Blocks are ordered (P-frame, channel Y/Cr/Cb, block row, block column); both streams run through the whole clip.
+//   dense : 3*H*W bytes per P-frame     packed : 3*H*W/8 (bitmaps) + ~nnz/2 + escapes + 24*H/8
 //
-// Kernels (HBM-bound streaming passes, one warp per block row, lanes = blocks, every load coalesced):
-//   pack_count_kernel   dense int8 planes -> bitmaps + row counts (stand-alone packing; in the encoder the DCT stage
-//                       emits both while it still holds the indices in registers, dct_stage.cuh)
-//   pack_scan_kernel    exclusive prefix of the row counts of one segment (single CTA) + running clip total
-//   pack_write_kernel   dense planes + bitmaps + row offsets -> value stream
+// Kernels (HBM-bound streaming passes, one warp per block row or per 32-block batch, lanes = blocks, coalesced):
+//   pack_count_kernel   dense int8 planes -> bitmaps, per-block escape counts, row counts (stand-alone packing; in the
+//                       encoder the DCT stage emits all three while it still holds the indices in registers)
+//   pack_scan_kernel    exclusive prefixes of the row counts of one segment (single CTA) + running clip totals
+//   pack_write_kernel   dense planes + bitmaps + offsets -> the two streams
 //   unpack_kernel       the exact inverse (decoder side)
 #pragma once
 #include "common.cuh"
 
 namespace vcs {
 
-// bitmap of the 8x8 block whose top-left byte is p (row pitch W); p is 8-byte aligned
-__device__ __forceinline__ unsigned long long block_bitmap(const int8_t *p, int W, uint2 rows[8]) {
+// bitmap and escape count of the 8x8 block whose top-left byte is p (row pitch W); p is 8-byte aligned
+__device__ __forceinline__ unsigned long long block_bitmap(const int8_t *p, int W, uint32_t &nesc) {
     unsigned long long bm = 0;
+    nesc = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        rows[i] = __ldg(reinterpret_cast<const uint2 *>(p + (size_t)i * W));
-        bm |= (unsigned long long)(nz_nibble(rows[i].x) | (nz_nibble(rows[i].y) << 4)) << (8 * i);
+        const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p + (size_t)i * W));
+        bm |= (unsigned long long)(nz_nibble(r.x) | (nz_nibble(r.y) << 4)) << (8 * i);
+        nesc += __popc(esc_nibble(r.x)) + __popc(esc_nibble(r.y));
     }
     return bm;
 }
 
 constexpr int PACK_WARPS = 8;
 
-// coef: [nrows_total/ (H/8)...] dense planes viewed as nrows = nP*3*(H/8) block rows of 8 x W bytes each
+// coef: dense planes viewed as nrows = nP*3*(H/8) block rows of 8 x W bytes each
 __global__ void __launch_bounds__(32 * PACK_WARPS)
 pack_count_kernel(const int8_t *__restrict__ coef, int W, int nrows, unsigned long long *__restrict__ bitmap,
-                  uint32_t *__restrict__ row_count) {
+                  uint8_t *__restrict__ blk_esc, uint2 *__restrict__ row_count) {
     const int lane = threadIdx.x & 31, nbx = W / 8;
     for (int row = blockIdx.x * PACK_WARPS + (threadIdx.x >> 5); row < nrows; row += gridDim.x * PACK_WARPS) {
         const int8_t *base = coef + (size_t)row * 8 * W;
-        uint32_t cnt = 0;
+        uint32_t nb = 0, ne = 0;
         for (int bx = lane; bx < nbx; bx += 32) {
-            uint2 rows[8];
-            const unsigned long long bm = block_bitmap(base + 8 * bx, W, rows);
+            uint32_t e;
+            const unsigned long long bm = block_bitmap(base + 8 * bx, W, e);
             bitmap[(size_t)row * nbx + bx] = bm;
-            cnt += __popcll(bm);
+            blk_esc[(size_t)row * nbx + bx] = (uint8_t)e;
+            nb += (__popcll(bm) + 1) >> 1;
+            ne += e;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) row_count[row] = cnt;
+        for (int o = 16; o > 0; o >>= 1) {
+            nb += __shfl_xor_sync(0xffffffffu, nb, o);
+            ne += __shfl_xor_sync(0xffffffffu, ne, o);
+        }
+        if (lane == 0) row_count[row] = make_uint2(nb, ne);
     }
 }
 
-// row_off[k] = *total + sum_{j<k} row_count[j] for the n rows of a segment; *total += sum.  One CTA.
+// off[k] = total + sum_{j<k} count[j] for both components of the n rows of a segment; totals += sums.  One CTA.
 __global__ void __launch_bounds__(1024)
-pack_scan_kernel(const uint32_t *__restrict__ row_count, int n, unsigned long long *__restrict__ row_off,
-                 unsigned long long *total, unsigned long long *seg_end) {
-    __shared__ unsigned long long warp_sum[32];
-    __shared__ unsigned long long carry;
+pack_scan_kernel(const uint2 *__restrict__ row_count, int n, unsigned long long *__restrict__ nib_off,
+                 unsigned long long *__restrict__ esc_off, unsigned long long *totals, unsigned long long *seg_end) {
+    __shared__ unsigned long long warp_sum[2][32];
+    __shared__ unsigned long long carry[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = *total;
+    if (threadIdx.x < 2) carry[threadIdx.x] = totals[threadIdx.x];
     __syncthreads();
     for (int k0 = 0; k0 < n; k0 += 1024) {
         const int k = k0 + threadIdx.x;
-        const unsigned long long v = k < n ? row_count[k] : 0;
-        unsigned long long s = v;
+        const uint2 c = k < n ? row_count[k] : make_uint2(0, 0);
+        const unsigned long long v[2] = {c.x, c.y};
+        unsigned long long s[2] = {v[0], v[1]};
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = shfl_up_u64(s, o);
-            if (lane >= o) s += t;
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = shfl_up_u64(s[q], o);
+                if (lane >= o) s[q] += t;
+            }
+            if (lane == 31) warp_sum[q][warp] = s[q];
         }
-        if (lane == 31) warp_sum[warp] = s;
         __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = warp_sum[lane];
+        if (warp < 2) {
+            unsigned long long w = warp_sum[warp][lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned long long t = shfl_up_u64(w, o);
                 if (lane >= o) w += t;
             }
-            warp_sum[lane] = w;          // inclusive over warps
+            warp_sum[warp][lane] = w;          // inclusive over warps
         }
         __syncthreads();
-        const unsigned long long before = carry + (warp ? warp_sum[warp - 1] : 0) + (s - v);
-        if (k < n) row_off[k] = before;
+        if (k < n) {
+            nib_off[k] = carry[0] + (warp ? warp_sum[0][warp - 1] : 0) + (s[0] - v[0]);
+            esc_off[k] = carry[1] + (warp ? warp_sum[1][warp - 1] : 0) + (s[1] - v[1]);
+        }
         __syncthreads();
-        if (threadIdx.x == 0) carry += warp_sum[31];
+        if (threadIdx.x < 2) carry[threadIdx.x] += warp_sum[threadIdx.x][31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) { *total = carry; if (seg_end) *seg_end = carry; }
+    if (threadIdx.x < 2) {
+        totals[threadIdx.x] = carry[threadIdx.x];
+        if (seg_end) seg_end[threadIdx.x] = carry[threadIdx.x];
+    }
 }
 
-// One warp per (block row, batch of 32 blocks).  The batch's values start at row_off[row] + the popcount of the row's
-// earlier bitmaps (read back, <= 7 coalesced loads per lane); lanes = blocks, a warp-wide prefix places each block.
-// A lane's values are a byte string at an arbitrary byte offset: written straight to global memory every store
-// instruction would touch 32 different sectors, so the warp first compacts its 32 blocks into shared memory and then
-// streams the contiguous run (<= 2 KB) out with one sector per store instruction.
+// One warp per (block row, batch of 32 blocks).  The batch starts at the row's offsets plus what the row's earlier
+// blocks hold (read back from the bitmaps and the per-block escape counts, <= 7 coalesced loads per lane); a warp-wide
+// prefix places each block.  A lane's output is a short byte string at an arbitrary byte offset: written straight to
+// global memory every store instruction would touch 32 different sectors, so the warp compacts its 32 blocks into
+// shared memory and streams the contiguous runs out with one sector per store instruction.
 __global__ void __launch_bounds__(32 * PACK_WARPS)
 pack_write_kernel(const int8_t *__restrict__ coef, int W, int nrows, const unsigned long long *__restrict__ bitmap,
-                  const unsigned long long *__restrict__ row_off, int8_t *__restrict__ values) {
-    __shared__ __align__(16) uint8_t stage[PACK_WARPS][32 * 64 + 16];
+                  const uint8_t *__restrict__ blk_esc, const unsigned long long *__restrict__ nib_off,
+                  const unsigned long long *__restrict__ esc_off, uint8_t *__restrict__ nibbles, int8_t *__restrict__ escapes) {
+    __shared__ __align__(16) uint8_t stage_n[PACK_WARPS][32 * 32];
+    __shared__ __align__(16) uint8_t stage_e[PACK_WARPS][32 * 64];
     const int lane = threadIdx.x & 31, nbx = W / 8, nbatch = (nbx + 31) / 32;
-    uint8_t *sw = stage[threadIdx.x >> 5];
+    uint8_t *sn = stage_n[threadIdx.x >> 5], *se = stage_e[threadIdx.x >> 5];
     const long long nitems = (long long)nrows * nbatch;
     for (long long item = (long long)blockIdx.x * PACK_WARPS + (threadIdx.x >> 5); item < nitems;
          item += (long long)gridDim.x * PACK_WARPS) {
         const int row = (int)(item / nbatch), bx0 = (int)(item - (long long)row * nbatch) * 32;
         const unsigned long long *bmrow = bitmap + (size_t)row * nbx;
-        uint32_t before = 0;
-        for (int b = lane; b < bx0; b += 32) before += __popcll(__ldg(bmrow + b));
+        const uint8_t *erow = blk_esc + (size_t)row * nbx;
+        uint32_t before_n = 0, before_e = 0;
+        for (int b = lane; b < bx0; b += 32) {
+            before_n += (__popcll(__ldg(bmrow + b)) + 1) >> 1;
+            before_e += __ldg(erow + b);
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            before_n += __shfl_xor_sync(0xffffffffu, before_n, o);
+            before_e += __shfl_xor_sync(0xffffffffu, before_e, o);
+        }
         const int bx = bx0 + lane;
         const unsigned long long bm = bx < nbx ? __ldg(bmrow + bx) : 0ull;
-        const uint32_t cnt = __popcll(bm);
-        uint32_t incl = cnt;
+        const uint32_t n = __popcll(bm), nb = (n + 1) >> 1, ne = bx < nbx ? __ldg(erow + bx) : 0u;
+        uint32_t incl = nb | (ne << 16);         // both prefixes in one scan: <= 1024 bytes and <= 2048 escapes per batch
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (cnt) {
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (n) {
             const int8_t *blk = coef + (size_t)row * 8 * W + 8 * bx;
-            uint8_t *dst = sw + (incl - cnt);
+            uint8_t *dn = sn + ((incl & 0xffffu) - nb), *de = se + ((incl >> 16) - ne);
+            uint32_t k = 0, lo = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if ((bm >> (8 * i)) & 0xffull) {
@@ -133,51 +163,79 @@ pack_write_kernel(const int8_t *__restrict__ coef, int W, int nrows, const unsig
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                        if (b) *dst++ = (uint8_t)b;
+                        if (b) {
+                            uint32_t code = b & 15u;
+                            if (((b + 8u) & 0xf0u) != 0) { code = 0; *de++ = (uint8_t)b; }     // outside [-8, 7]
+                            if (k & 1) *dn++ = (uint8_t)(lo | (code << 4)); else lo = code;
+                            ++k;
+                        }
                     }
                 }
             }
+            if (k & 1) *dn = (uint8_t)lo;
         }
         __syncwarp();
-        int8_t *g = values + row_off[row] + before;
-        for (uint32_t k = lane; k < total; k += 32) g[k] = (int8_t)sw[k];
+        uint8_t *gn = nibbles + nib_off[row] + before_n;
+        for (uint32_t q = lane; q < (tot & 0xffffu); q += 32) gn[q] = sn[q];
+        int8_t *ge = escapes + esc_off[row] + before_e;
+        for (uint32_t q = lane; q < (tot >> 16); q += 32) ge[q] = (int8_t)se[q];
         __syncwarp();
     }
 }
 
-// inverse: bitmaps + row offsets + value stream -> dense int8 planes (every byte of the planes is written)
+// inverse: bitmaps + row offsets + the two streams -> dense int8 planes (every byte of the planes is written).  One
+// warp per block row, batches in sequence (a block's escape count is only known once its nibbles have been read).
 __global__ void __launch_bounds__(32 * PACK_WARPS)
-unpack_kernel(const unsigned long long *__restrict__ bitmap, const unsigned long long *__restrict__ row_off,
-              const int8_t *__restrict__ values, unsigned long long nvalues, int W, int nrows,
+unpack_kernel(const unsigned long long *__restrict__ bitmap, const unsigned long long *__restrict__ nib_off,
+              const unsigned long long *__restrict__ esc_off, const uint8_t *__restrict__ nibbles,
+              unsigned long long nnib, const int8_t *__restrict__ escapes, unsigned long long nesc, int W, int nrows,
               int8_t *__restrict__ coef, int *err) {
     const int lane = threadIdx.x & 31, nbx = W / 8;
     for (int row = blockIdx.x * PACK_WARPS + (threadIdx.x >> 5); row < nrows; row += gridDim.x * PACK_WARPS) {
         int8_t *base = coef + (size_t)row * 8 * W;
-        unsigned long long off = row_off[row];
+        unsigned long long off_n = nib_off[row], off_e = esc_off[row];
         for (int bx0 = 0; bx0 < nbx; bx0 += 32) {
             const int bx = bx0 + lane;
             const unsigned long long bm = bx < nbx ? __ldg(bitmap + (size_t)row * nbx + bx) : 0ull;
-            const uint32_t cnt = __popcll(bm);
-            uint32_t incl = cnt;
+            const uint32_t n = __popcll(bm), nb = (n + 1) >> 1;
+            uint32_t incl = nb;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += t;
             }
-            unsigned long long src = off + (incl - cnt);
+            const unsigned long long src_n = off_n + (incl - nb);
+            bool ok = src_n + nb <= nnib;                   // a damaged stream is never read past its end
+            uint32_t ne = 0;                                // escapes of this block = zero codes among its n nibbles
+            if (ok)
+                for (uint32_t k = 0; k < n; ++k) ne += ((__ldg(nibbles + src_n + (k >> 1)) >> (4 * (k & 1))) & 15u) == 0;
+            uint32_t incl_e = ne;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl_e, o);
+                if (lane >= o) incl_e += t;
+            }
+            unsigned long long src_e = off_e + (incl_e - ne);
+            ok = ok && src_e + ne <= nesc;
             if (bx < nbx) {
-                const bool ok = src + cnt <= nvalues;       // a damaged stream is never read past its end
                 if (!ok && err) *(volatile int *)err = 2;
+                uint32_t k = 0;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     uint32_t w[2] = {0, 0};
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (ok && ((bm >> (8 * i + j)) & 1)) w[j >> 2] |= (uint32_t)(uint8_t)__ldg(values + src++) << (8 * (j & 3));
+                        if (ok && ((bm >> (8 * i + j)) & 1)) {
+                            const uint32_t code = (__ldg(nibbles + src_n + (k >> 1)) >> (4 * (k & 1))) & 15u;
+                            ++k;
+                            const uint32_t v = code ? ((code ^ 8u) - 8u) & 0xffu : (uint32_t)(uint8_t)__ldg(escapes + src_e++);
+                            w[j >> 2] |= v << (8 * (j & 3));
+                        }
                     *reinterpret_cast<uint2 *>(base + (size_t)i * W + 8 * bx) = make_uint2(w[0], w[1]);
                 }
             }
-            off += __shfl_sync(0xffffffffu, incl, 31);
+            off_n += __shfl_sync(0xffffffffu, incl, 31);
+            off_e += __shfl_sync(0xffffffffu, incl_e, 31);
         }
     }
 }

@@ -27,9 +27,9 @@ using namespace vcs;
 
 namespace {
 
-constexpr int NUM_DEV_SLOTS = 17;
+constexpr int NUM_DEV_SLOTS = 19;
 enum DevSlot { S_FRAMES = 0, S_MV, S_COST, S_FLAGS, S_COEF, S_RECON, S_AUX0, S_AUX1, S_AUX2, S_MB, S_CYC,
-               S_PK_BITMAP, S_PK_ROWCNT, S_PK_ROWOFF, S_PK_VALUES, S_PK_TOTAL };
+               S_PK_BITMAP, S_PK_ROWCNT, S_PK_ROWOFF, S_PK_VALUES, S_PK_TOTAL, S_PK_BLKESC, S_PK_ESC };
 
 struct EvTriple {
     cudaEvent_t e0, e1, e2;
@@ -266,7 +266,7 @@ EvTriple *next_events(vcs_ctx *ctx) {
 // ME + residual/DCT/recon for nP P-frames addressed by fa, on stream st.
 int encode_dev(vcs_ctx *ctx, cudaStream_t st, const vcs_me_params *p, const FrameAddr &fa, int nP,
                int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef, uint8_t *recon,
-               unsigned long long *bitmap = nullptr, uint32_t *row_count = nullptr) {
+               unsigned long long *bitmap = nullptr, uint8_t *blk_esc = nullptr, uint2 *row_count = nullptr) {
     EvTriple *ev = next_events(ctx);
     if (ev) CK(ctx, cudaEventRecord(ev->e0, st));
     int rc = launch_me(ctx, st, p, fa, nP, mv, cost, flags);
@@ -278,10 +278,11 @@ int encode_dev(vcs_ctx *ctx, cudaStream_t st, const vcs_me_params *p, const Fram
         a.H = p->H; a.W = p->W; a.fa = fa; a.has_fa = 1; a.mv = mv; a.bs = p->bs;
         a.nbx = p->W / p->bs; a.nby = p->H / p->bs; a.forward = 1; a.inverse = recon != nullptr;
         a.coef_mode = coef_mode; a.coef = coef; a.recon = recon;
-        if (bitmap && row_count && coef && !recon && coef_mode == VCS_COEF_I8_RINT) {   // forward-only variant of the kernel
-            // the DCT stage emits the occupancy bitmaps and (atomically) the per-block-row counts of the packed form
-            a.bitmap = reinterpret_cast<uint8_t *>(bitmap); a.row_count = row_count;
-            CK(ctx, cudaMemsetAsync(row_count, 0, sizeof(uint32_t) * (size_t)nP * 3 * (p->H / 8), st));
+        if (bitmap && blk_esc && row_count && coef && !recon && coef_mode == VCS_COEF_I8_RINT) {   // forward-only variant of the kernel
+            // the DCT stage emits the occupancy bitmaps, escape counts and (atomically) the per-block-row counts
+            a.bitmap = reinterpret_cast<uint8_t *>(bitmap); a.blk_esc = blk_esc;
+            a.row_count = reinterpret_cast<unsigned long long *>(row_count);
+            CK(ctx, cudaMemsetAsync(row_count, 0, sizeof(uint2) * (size_t)nP * 3 * (p->H / 8), st));
         }
         rc = launch_dct(ctx, st, a, nP);
         if (rc) return rc;
@@ -290,38 +291,70 @@ int encode_dev(vcs_ctx *ctx, cudaStream_t st, const vcs_me_params *p, const Fram
     return VCS_OK;
 }
 
-// ---- packed coefficient stream (pack.cuh) ----------------------------------------------------------------
+// ---- packed coefficient streams (pack.cuh) ---------------------------------------------------------------
 struct PackedHost {              // host destinations of vcs_encode_clip_host_packed
     unsigned long long *bitmap;  // [nP][3][H/8][W/8]
-    uint32_t *row_count;         // [nP][3][H/8]
-    int8_t *values;              // value stream, capacity bytes
-    size_t capacity;
-    unsigned long long *nvalues; // out: length of the stream
+    uint32_t *row_count;         // [nP][3][H/8][2]
+    uint8_t *nibbles;            // nibble stream, cap_n bytes
+    size_t cap_n;
+    int8_t *escapes;             // escape stream, cap_e bytes
+    size_t cap_e;
+    unsigned long long *lengths; // out: [2] = bytes of the nibble stream, number of escapes
 };
 
-static int pack_grid(vcs_ctx *ctx, int nrows) {
-    long long g = ((long long)nrows + PACK_WARPS - 1) / PACK_WARPS;
+struct PackedDev {               // device side of one clip (or of one stand-alone pack call)
+    unsigned long long *bitmap;  // [rows][W/8]
+    uint8_t *blk_esc;            // [rows][W/8]
+    uint2 *row_count;            // [rows]
+    unsigned long long *nib_off, *esc_off;   // [rows]
+    uint8_t *nibbles;
+    int8_t *escapes;
+    unsigned long long *totals;  // [2] running lengths
+};
+
+static int pack_grid(vcs_ctx *ctx, long long nwarps) {
+    long long g = (nwarps + PACK_WARPS - 1) / PACK_WARPS;
     const long long cap = (long long)ctx->sm_count * 8;
     return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
-// dense int8 planes of nP frames -> bitmaps, row counts, row offsets and values on the device.  *d_total (device,
-// 8 bytes) is the running stream length: the rows of this call are appended after it.  d_segend (device or mapped,
-// may be null) receives the new total.
-static int launch_pack(vcs_ctx *ctx, cudaStream_t st, int H, int W, int nP, const int8_t *coef,
-                       unsigned long long *d_bitmap, uint32_t *d_rowcnt, unsigned long long *d_rowoff,
-                       int8_t *d_values, unsigned long long *d_total, unsigned long long *d_segend, bool have_bitmaps) {
-    const int nrows = nP * 3 * (H / 8);
+// dense int8 planes of nP frames -> the packed form on the device, rows [row0, row0 + nP*3*H/8) of d.  d.totals (device,
+// 2 x 8 bytes) are the running stream lengths: this call's rows are appended after them.  d_segend (device, 2 x 8
+// bytes, may be null) receives the new totals.  have_bitmaps: the DCT stage already wrote bitmaps, escape counts and
+// row counts for these rows.
+static int launch_pack(vcs_ctx *ctx, cudaStream_t st, int H, int W, int nP, const int8_t *coef, const PackedDev &d,
+                       size_t row0, unsigned long long *d_segend, bool have_bitmaps) {
+    const int nrows = nP * 3 * (H / 8), nbx = W / 8;
     if (nrows <= 0) return VCS_OK;
-    const int nbatch = (W / 8 + 31) / 32;
-    if (!have_bitmaps) {     // the DCT stage did not produce them (stand-alone packing of given planes)
-        pack_count_kernel<<<pack_grid(ctx, nrows), 32 * PACK_WARPS, 0, st>>>(coef, W, nrows, d_bitmap, d_rowcnt);
+    const int nbatch = (nbx + 31) / 32;
+    if (!have_bitmaps) {     // stand-alone packing of given planes
+        pack_count_kernel<<<pack_grid(ctx, nrows), 32 * PACK_WARPS, 0, st>>>(coef, W, nrows, d.bitmap + row0 * nbx,
+                                                                            d.blk_esc + row0 * nbx, d.row_count + row0);
         ctx->launches += 1;
     }
-    pack_scan_kernel<<<1, 1024, 0, st>>>(d_rowcnt, nrows, d_rowoff, d_total, d_segend);
-    pack_write_kernel<<<pack_grid(ctx, nrows * nbatch), 32 * PACK_WARPS, 0, st>>>(coef, W, nrows, d_bitmap, d_rowoff, d_values);
+    pack_scan_kernel<<<1, 1024, 0, st>>>(d.row_count + row0, nrows, d.nib_off + row0, d.esc_off + row0, d.totals, d_segend);
+    pack_write_kernel<<<pack_grid(ctx, (long long)nrows * nbatch), 32 * PACK_WARPS, 0, st>>>(
+        coef, W, nrows, d.bitmap + row0 * nbx, d.blk_esc + row0 * nbx, d.nib_off + row0, d.esc_off + row0, d.nibbles, d.escapes);
     CK(ctx, cudaGetLastError());
     ctx->launches += 2;
+    return VCS_OK;
+}
+
+// scratch of the packed form for `rows` block rows of W/8 blocks; `dense` = bytes of the dense planes they code
+static int packed_scratch(vcs_ctx *ctx, size_t rows, int W, size_t dense, int nsegs, PackedDev &d) {
+    int rc;
+    const size_t nbx = (size_t)W / 8;
+    if ((rc = dev_buf(ctx, S_PK_BITMAP, rows * nbx * 8 + 8, (void **)&d.bitmap))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_BLKESC, rows * nbx + 8, (void **)&d.blk_esc))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_ROWCNT, rows * 8 + 8, (void **)&d.row_count))) return rc;
+    unsigned long long *off;
+    if ((rc = dev_buf(ctx, S_PK_ROWOFF, rows * 16 + 16, (void **)&off))) return rc;
+    d.nib_off = off; d.esc_off = off + rows;
+    if ((rc = dev_buf(ctx, S_PK_VALUES, dense / 2 + rows * nbx + 64, (void **)&d.nibbles))) return rc;   // <= 32 bytes per block
+    if ((rc = dev_buf(ctx, S_PK_ESC, dense + 64, (void **)&d.escapes))) return rc;
+    // [0..1]: running totals; [2 + 2c .. 3 + 2c]: their values after segment c (a private slot per segment: the
+    // download stream may read it while the compute stream is already extending the streams for the next segment)
+    if ((rc = dev_buf(ctx, S_PK_TOTAL, 16 * (size_t)(nsegs + 1), (void **)&d.totals))) return rc;
     return VCS_OK;
 }
 
@@ -832,16 +865,10 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
     if ((rc = dev_buf(ctx, S_FLAGS, (size_t)nP * N + 4, (void **)&d_fl))) return rc;
     if ((coef || pk) && (rc = dev_buf(ctx, S_COEF, (size_t)nP * npix * 3 * ce + 8, &d_coef))) return rc;
     if (recon && (rc = dev_buf(ctx, S_RECON, (size_t)nP * fs + 4, (void **)&d_rec))) return rc;
-    // packed sink: the dense int8 planes stay on the device, bitmaps + row counts + the value stream travel
+    // packed sink: the dense int8 planes stay on the device; bitmaps, row counts and the two streams travel
     const int rows_per_p = 3 * (p->H / 8), nbx8 = p->W / 8;
-    unsigned long long *d_bitmap = nullptr, *d_rowoff = nullptr, *d_total = nullptr;
-    uint32_t *d_rowcnt = nullptr; int8_t *d_values = nullptr;
-    if (pk) {
-        if ((rc = dev_buf(ctx, S_PK_BITMAP, (size_t)nP * rows_per_p * nbx8 * 8 + 8, (void **)&d_bitmap))) return rc;
-        if ((rc = dev_buf(ctx, S_PK_ROWCNT, (size_t)nP * rows_per_p * 4 + 4, (void **)&d_rowcnt))) return rc;
-        if ((rc = dev_buf(ctx, S_PK_ROWOFF, (size_t)nP * rows_per_p * 8 + 8, (void **)&d_rowoff))) return rc;
-        if ((rc = dev_buf(ctx, S_PK_VALUES, (size_t)nP * npix * 3 + 64, (void **)&d_values))) return rc;
-    }
+    PackedDev pd;
+    memset(&pd, 0, sizeof(pd));
 
     // Pipeline: copy-in on s_h2d, kernels on the compute stream, copy-out on s_d2h, chained with events; PCIe
     // is full duplex so the three overlap.  Segments are ranges of P-frames (they may start and end inside a GOP):
@@ -897,7 +924,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
         if ((size_t)nsegs > ctx->h_segend_cap) {
             if (ctx->h_segend) cudaFreeHost(ctx->h_segend);
             ctx->h_segend = nullptr; ctx->h_segend_cap = 0;
-            CK(ctx, cudaHostAlloc((void **)&ctx->h_segend, sizeof(unsigned long long) * (size_t)nsegs, cudaHostAllocDefault));
+            CK(ctx, cudaHostAlloc((void **)&ctx->h_segend, 2 * sizeof(unsigned long long) * (size_t)nsegs, cudaHostAllocDefault));
             ctx->h_segend_cap = (size_t)nsegs;
         }
         while ((int)ctx->seg_events.size() < nsegs) {
@@ -905,11 +932,9 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
             CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ctx->seg_events.push_back(e);
         }
-        // [0]: running stream length; [1 + c]: its value after segment c (a private slot per segment: the download
-        // stream may read it while the compute stream is already extending the stream for the next segment)
-        if ((rc = dev_buf(ctx, S_PK_TOTAL, 8 * (size_t)(nsegs + 1), (void **)&d_total))) return rc;
-        CK(ctx, cudaMemsetAsync(d_total, 0, 8, ctx->stream));
-        *pk->nvalues = 0;
+        if ((rc = packed_scratch(ctx, (size_t)nP * rows_per_p, p->W, (size_t)nP * npix * 3, nsegs, pd))) return rc;
+        CK(ctx, cudaMemsetAsync(pd.totals, 0, 16, ctx->stream));
+        pk->lengths[0] = pk->lengths[1] = 0;
     }
     while ((int)ctx->chunk_events.size() < 2 * nsegs) {
         cudaEvent_t e;
@@ -966,19 +991,19 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
                             d_fl + (size_t)p0 * N,
                             d_coef ? (void *)((char *)d_coef + (size_t)p0 * npix * 3 * ce) : nullptr,
                             d_rec ? d_rec + (size_t)p0 * fs : nullptr,
-                            pk ? d_bitmap + (size_t)p0 * rows_per_p * nbx8 : nullptr,
-                            pk ? d_rowcnt + (size_t)p0 * rows_per_p : nullptr);
+                            pk ? pd.bitmap + (size_t)p0 * rows_per_p * nbx8 : nullptr,
+                            pk ? pd.blk_esc + (size_t)p0 * rows_per_p * nbx8 : nullptr,
+                            pk ? pd.row_count + (size_t)p0 * rows_per_p : nullptr);
             if (rc) return rc;
-            if (pk && (rc = launch_pack(ctx, sc, p->H, p->W, np, (const int8_t *)d_coef + (size_t)p0 * npix * 3,
-                                        d_bitmap + (size_t)p0 * rows_per_p * nbx8, d_rowcnt + (size_t)p0 * rows_per_p,
-                                        d_rowoff + (size_t)p0 * rows_per_p, d_values, d_total, d_total + 1 + c, d_rec == nullptr)))
+            if (pk && (rc = launch_pack(ctx, sc, p->H, p->W, np, (const int8_t *)d_coef + (size_t)p0 * npix * 3, pd,
+                                        (size_t)p0 * rows_per_p, pd.totals + 2 + 2 * c, d_rec == nullptr)))
                 return rc;
         }
         CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sc));
         tmark(sc);           // 3 + 4c: compute of segment c done
         if (pk) {
             CK(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->chunk_events[2 * c + 1], 0));
-            CK(ctx, cudaMemcpyAsync(&ctx->h_segend[c], d_total + 1 + c, 8, cudaMemcpyDeviceToHost, ctx->s_aux));
+            CK(ctx, cudaMemcpyAsync(&ctx->h_segend[2 * c], pd.totals + 2 + 2 * c, 16, cudaMemcpyDeviceToHost, ctx->s_aux));
             CK(ctx, cudaEventRecord(ctx->seg_events[c], ctx->s_aux));
         } else {
             CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->chunk_events[2 * c + 1], 0));
@@ -988,26 +1013,29 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
         p0 += np;
     }
     if (!pk) return VCS_OK;
-    unsigned long long host_values = 0;      // bytes of the value stream already queued for download
+    unsigned long long have_n = 0, have_e = 0;      // bytes of the two streams already queued for download
     p0 = 0;
     for (int c = 0; c < nsegs; ++c) {
         const int np = sizes[c];
-        CK(ctx, cudaEventSynchronize(ctx->seg_events[c]));       // segment c is complete and its stream length is here
-        const unsigned long long end = ctx->h_segend[c];
-        if (end > pk->capacity) return fail(ctx, VCS_E_INVALID, "value buffer too small (%llu > %zu bytes)", end, pk->capacity);
+        CK(ctx, cudaEventSynchronize(ctx->seg_events[c]));       // segment c is complete and its stream lengths are here
+        const unsigned long long end_n = ctx->h_segend[2 * c], end_e = ctx->h_segend[2 * c + 1];
+        if (end_n > pk->cap_n || end_e > pk->cap_e)
+            return fail(ctx, VCS_E_INVALID, "packed output buffers too small (nibbles %llu > %zu or escapes %llu > %zu bytes)",
+                        end_n, pk->cap_n, end_e, pk->cap_e);
         if (np > 0) {
-            if (end > host_values)
-                CK(ctx, cudaMemcpyAsync(pk->values + host_values, d_values + host_values, end - host_values,
-                                        cudaMemcpyDeviceToHost, ctx->s_d2h));
-            CK(ctx, cudaMemcpyAsync(pk->bitmap + (size_t)p0 * rows_per_p * nbx8, d_bitmap + (size_t)p0 * rows_per_p * nbx8,
+            if (end_n > have_n)
+                CK(ctx, cudaMemcpyAsync(pk->nibbles + have_n, pd.nibbles + have_n, end_n - have_n, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (end_e > have_e)
+                CK(ctx, cudaMemcpyAsync(pk->escapes + have_e, pd.escapes + have_e, end_e - have_e, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(ctx, cudaMemcpyAsync(pk->bitmap + (size_t)p0 * rows_per_p * nbx8, pd.bitmap + (size_t)p0 * rows_per_p * nbx8,
                                     (size_t)np * rows_per_p * nbx8 * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
-            CK(ctx, cudaMemcpyAsync(pk->row_count + (size_t)p0 * rows_per_p, d_rowcnt + (size_t)p0 * rows_per_p,
-                                    (size_t)np * rows_per_p * 4, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(ctx, cudaMemcpyAsync(pk->row_count + (size_t)p0 * rows_per_p * 2, pd.row_count + (size_t)p0 * rows_per_p,
+                                    (size_t)np * rows_per_p * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
             if ((rc = download(p0, np))) return rc;
         }
         tmark(ctx->s_d2h);       // 4 + 4c (packed sink: appended after the pass-1 marks): download of segment c done
-        host_values = end;
-        *pk->nvalues = host_values;
+        have_n = end_n; have_e = end_e;
+        pk->lengths[0] = have_n; pk->lengths[1] = have_e;
         p0 += np;
     }
     return VCS_OK;
@@ -1041,53 +1069,64 @@ int vcs_encode_clip_host(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *fr
 
 int vcs_encode_clip_host_packed(vcs_ctx *ctx, const vcs_me_params *p, const uint8_t *frames, int T, int gop_len,
                                 int16_t *mv, uint32_t *cost, uint8_t *flags, uint64_t *bitmap, uint32_t *row_count,
-                                int8_t *values, size_t values_capacity, uint64_t *nvalues, uint8_t *recon) {
+                                uint8_t *nibbles, size_t nibbles_capacity, int8_t *escapes, size_t escapes_capacity,
+                                uint64_t *lengths, uint8_t *recon) {
     if (!ctx) return VCS_E_INVALID;
-    if (!bitmap || !row_count || !values || !nvalues) return fail(ctx, VCS_E_INVALID, "NULL packed output");
-    PackedHost pk{(unsigned long long *)bitmap, row_count, values, values_capacity, (unsigned long long *)nvalues};
+    if (!bitmap || !row_count || !nibbles || !escapes || !lengths) return fail(ctx, VCS_E_INVALID, "NULL packed output");
+    PackedHost pk{(unsigned long long *)bitmap, row_count, nibbles, nibbles_capacity, escapes, escapes_capacity,
+                  (unsigned long long *)lengths};
     return encode_clip_host_impl(ctx, p, frames, T, gop_len, VCS_COEF_I8_RINT, mv, cost, flags, nullptr, recon, &pk);
 }
 
 // dense int8 index planes [nP][3][H][W] (device) -> packed form (device): bitmap [nP][3][H/8][W/8], row_count
-// [nP][3][H/8], values (capacity 3*H*W*nP bytes is always enough), *nvalues_host = stream length (synchronises).
+// [nP][3][H/8][2], nibbles (3*H*W*nP/2 + one byte per 2 blocks is always enough), escapes (3*H*W*nP is always enough);
+// lengths_host[2] = bytes of the nibble stream, number of escapes (synchronises).
 int vcs_pack_coef_dev(vcs_ctx *ctx, int H, int W, int nP, const int8_t *coef, uint64_t *bitmap, uint32_t *row_count,
-                      int8_t *values, uint64_t *nvalues_host) {
+                      uint8_t *nibbles, int8_t *escapes, uint64_t *lengths_host) {
     VCS_ENTER(ctx);
-    if (!coef || !bitmap || !row_count || !values || !nvalues_host || H <= 0 || W <= 0 || H % 8 || W % 8 || nP < 0)
+    if (!coef || !bitmap || !row_count || !nibbles || !escapes || !lengths_host || H <= 0 || W <= 0 || H % 8 || W % 8 || nP < 0)
         return fail(ctx, VCS_E_INVALID, "bad pack arguments");
-    if (((uintptr_t)coef | (uintptr_t)bitmap) & 7) return fail(ctx, VCS_E_INVALID, "coef and bitmap must be 8-byte aligned");
-    unsigned long long *d_rowoff, *d_total; int rc;
-    const int nrows = nP * 3 * (H / 8);
-    if ((rc = dev_buf(ctx, S_PK_ROWOFF, (size_t)nrows * 8 + 8, (void **)&d_rowoff))) return rc;
-    if ((rc = dev_buf(ctx, S_PK_TOTAL, 8, (void **)&d_total))) return rc;
+    if (((uintptr_t)coef | (uintptr_t)bitmap | (uintptr_t)row_count) & 7)
+        return fail(ctx, VCS_E_INVALID, "coef, bitmap and row_count must be 8-byte aligned");
+    const size_t nrows = (size_t)nP * 3 * (H / 8), nbx = (size_t)W / 8;
+    PackedDev d; int rc;
+    memset(&d, 0, sizeof(d));
+    d.bitmap = (unsigned long long *)bitmap; d.row_count = (uint2 *)row_count; d.nibbles = nibbles; d.escapes = escapes;
+    unsigned long long *off;
+    if ((rc = dev_buf(ctx, S_PK_BLKESC, nrows * nbx + 8, (void **)&d.blk_esc))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_ROWOFF, nrows * 16 + 16, (void **)&off))) return rc;
+    d.nib_off = off; d.esc_off = off + nrows;
+    if ((rc = dev_buf(ctx, S_PK_TOTAL, 16, (void **)&d.totals))) return rc;
     cudaStream_t st = ctx->stream;
-    CK(ctx, cudaMemsetAsync(d_total, 0, 8, st));
-    if ((rc = launch_pack(ctx, st, H, W, nP, coef, (unsigned long long *)bitmap, row_count, d_rowoff, values, d_total, nullptr, false)))
-        return rc;
-    unsigned long long tot = 0;
-    CK(ctx, cudaMemcpyAsync(&tot, d_total, 8, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemsetAsync(d.totals, 0, 16, st));
+    if ((rc = launch_pack(ctx, st, H, W, nP, coef, d, 0, nullptr, false))) return rc;
+    unsigned long long tot[2] = {0, 0};
+    CK(ctx, cudaMemcpyAsync(tot, d.totals, 16, cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaStreamSynchronize(st));
-    *nvalues_host = tot;
+    lengths_host[0] = tot[0]; lengths_host[1] = tot[1];
     return VCS_OK;
 }
 
 // the exact inverse, all device pointers; enqueued on the context's stream
 int vcs_unpack_coef_dev(vcs_ctx *ctx, int H, int W, int nP, const uint64_t *bitmap, const uint32_t *row_count,
-                        const int8_t *values, uint64_t nvalues, int8_t *coef) {
+                        const uint8_t *nibbles, uint64_t nnibble_bytes, const int8_t *escapes, uint64_t nescapes,
+                        int8_t *coef) {
     VCS_ENTER(ctx);
-    if (!coef || !bitmap || !row_count || (!values && nvalues) || H <= 0 || W <= 0 || H % 8 || W % 8 || nP < 0)
+    if (!coef || !bitmap || !row_count || (!nibbles && nnibble_bytes) || (!escapes && nescapes) || H <= 0 || W <= 0 ||
+        H % 8 || W % 8 || nP < 0)
         return fail(ctx, VCS_E_INVALID, "bad unpack arguments");
-    if (((uintptr_t)coef | (uintptr_t)bitmap) & 7) return fail(ctx, VCS_E_INVALID, "coef and bitmap must be 8-byte aligned");
-    unsigned long long *d_rowoff, *d_total; int rc;
+    if (((uintptr_t)coef | (uintptr_t)bitmap | (uintptr_t)row_count) & 7)
+        return fail(ctx, VCS_E_INVALID, "coef, bitmap and row_count must be 8-byte aligned");
     const int nrows = nP * 3 * (H / 8);
     if (nrows == 0) return VCS_OK;
-    if ((rc = dev_buf(ctx, S_PK_ROWOFF, (size_t)nrows * 8 + 8, (void **)&d_rowoff))) return rc;
-    if ((rc = dev_buf(ctx, S_PK_TOTAL, 8, (void **)&d_total))) return rc;
+    unsigned long long *off, *d_total; int rc;
+    if ((rc = dev_buf(ctx, S_PK_ROWOFF, (size_t)nrows * 16 + 16, (void **)&off))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_TOTAL, 16, (void **)&d_total))) return rc;
     cudaStream_t st = ctx->stream;
-    CK(ctx, cudaMemsetAsync(d_total, 0, 8, st));
-    pack_scan_kernel<<<1, 1024, 0, st>>>(row_count, nrows, d_rowoff, d_total, nullptr);
-    unpack_kernel<<<pack_grid(ctx, nrows), 32 * PACK_WARPS, 0, st>>>((const unsigned long long *)bitmap, d_rowoff, values,
-                                                                    nvalues, W, nrows, coef, ctx->h_errflag);
+    CK(ctx, cudaMemsetAsync(d_total, 0, 16, st));
+    pack_scan_kernel<<<1, 1024, 0, st>>>((const uint2 *)row_count, nrows, off, off + nrows, d_total, nullptr);
+    unpack_kernel<<<pack_grid(ctx, nrows), 32 * PACK_WARPS, 0, st>>>((const unsigned long long *)bitmap, off, off + nrows, nibbles,
+                                                                    nnibble_bytes, escapes, nescapes, W, nrows, coef, ctx->h_errflag);
     CK(ctx, cudaGetLastError());
     ctx->launches += 2;
     return VCS_OK;
@@ -1096,7 +1135,8 @@ int vcs_unpack_coef_dev(vcs_ctx *ctx, int H, int W, int nP, const uint64_t *bitm
 // Decoder side from the packed form, host buffers: upload, unpack, then vcs_decode_clip_dev's kernel.
 int vcs_decode_clip_host_packed(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_frames, int T, int gop_len,
                                 const int16_t *mv, const uint64_t *bitmap, const uint32_t *row_count,
-                                const int8_t *values, uint64_t nvalues, uint8_t *recon) {
+                                const uint8_t *nibbles, uint64_t nnibble_bytes, const int8_t *escapes, uint64_t nescapes,
+                                uint8_t *recon) {
     VCS_ENTER(ctx);
     if (!ref_frames || !mv || !bitmap || !row_count || !recon || gop_len < 2 || T < 1 || bs <= 0 || H < bs || W < bs)
         return fail(ctx, VCS_E_INVALID, "bad decode arguments");
@@ -1110,24 +1150,29 @@ int vcs_decode_clip_host_packed(vcs_ctx *ctx, int H, int W, int bs, const uint8_
             return fail(ctx, VCS_E_INVALID, "motion vector %lld points outside the frame", k);
     }
     const size_t nrows = (size_t)nP * 3 * (H / 8), nbx8 = W / 8;
-    unsigned long long tot = 0;
-    for (size_t k = 0; k < nrows; ++k) tot += row_count[k];
-    if (tot != nvalues) return fail(ctx, VCS_E_INVALID, "row counts (%llu) do not add up to the stream length (%llu)", tot, (unsigned long long)nvalues);
-    uint8_t *d_ref, *d_rec; int16_t *d_mv; int8_t *d_coef, *d_values; unsigned long long *d_bitmap; uint32_t *d_rowcnt; int rc;
+    unsigned long long tot_n = 0, tot_e = 0;
+    for (size_t k = 0; k < nrows; ++k) { tot_n += row_count[2 * k]; tot_e += row_count[2 * k + 1]; }
+    if (tot_n != nnibble_bytes || tot_e != nescapes)
+        return fail(ctx, VCS_E_INVALID, "row counts (%llu, %llu) do not add up to the stream lengths (%llu, %llu)", tot_n, tot_e,
+                    (unsigned long long)nnibble_bytes, (unsigned long long)nescapes);
+    uint8_t *d_ref, *d_rec, *d_nib; int16_t *d_mv; int8_t *d_coef, *d_esc; unsigned long long *d_bitmap; uint32_t *d_rowcnt; int rc;
     if ((rc = dev_buf(ctx, S_FRAMES, fs * nG, (void **)&d_ref))) return rc;
     if ((rc = dev_buf(ctx, S_MV, (size_t)nP * N * 4 + 4, (void **)&d_mv))) return rc;
     if ((rc = dev_buf(ctx, S_COEF, (size_t)nP * npix * 3 + 8, (void **)&d_coef))) return rc;
     if ((rc = dev_buf(ctx, S_RECON, (size_t)nP * fs + 4, (void **)&d_rec))) return rc;
     if ((rc = dev_buf(ctx, S_PK_BITMAP, nrows * nbx8 * 8 + 8, (void **)&d_bitmap))) return rc;
-    if ((rc = dev_buf(ctx, S_PK_ROWCNT, nrows * 4 + 4, (void **)&d_rowcnt))) return rc;
-    if ((rc = dev_buf(ctx, S_PK_VALUES, (size_t)nvalues + 64, (void **)&d_values))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_ROWCNT, nrows * 8 + 8, (void **)&d_rowcnt))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_VALUES, (size_t)nnibble_bytes + 64, (void **)&d_nib))) return rc;
+    if ((rc = dev_buf(ctx, S_PK_ESC, (size_t)nescapes + 64, (void **)&d_esc))) return rc;
     cudaStream_t st = ctx->stream;
     CK(ctx, cudaMemcpyAsync(d_ref, ref_frames, fs * nG, cudaMemcpyHostToDevice, st));
     CK(ctx, cudaMemcpyAsync(d_mv, mv, (size_t)nP * N * 4, cudaMemcpyHostToDevice, st));
     CK(ctx, cudaMemcpyAsync(d_bitmap, bitmap, nrows * nbx8 * 8, cudaMemcpyHostToDevice, st));
-    CK(ctx, cudaMemcpyAsync(d_rowcnt, row_count, nrows * 4, cudaMemcpyHostToDevice, st));
-    if (nvalues) CK(ctx, cudaMemcpyAsync(d_values, values, (size_t)nvalues, cudaMemcpyHostToDevice, st));
-    if ((rc = vcs_unpack_coef_dev(ctx, H, W, nP, (const uint64_t *)d_bitmap, d_rowcnt, d_values, nvalues, d_coef))) return rc;
+    CK(ctx, cudaMemcpyAsync(d_rowcnt, row_count, nrows * 8, cudaMemcpyHostToDevice, st));
+    if (nnibble_bytes) CK(ctx, cudaMemcpyAsync(d_nib, nibbles, (size_t)nnibble_bytes, cudaMemcpyHostToDevice, st));
+    if (nescapes) CK(ctx, cudaMemcpyAsync(d_esc, escapes, (size_t)nescapes, cudaMemcpyHostToDevice, st));
+    if ((rc = vcs_unpack_coef_dev(ctx, H, W, nP, (const uint64_t *)d_bitmap, d_rowcnt, d_nib, nnibble_bytes, d_esc, nescapes, d_coef)))
+        return rc;
     if ((rc = vcs_decode_clip_dev(ctx, H, W, bs, d_ref, T, gop_len, d_mv, VCS_COEF_I8_RINT, d_coef, d_rec))) return rc;
     CK(ctx, cudaMemcpyAsync(recon, d_rec, (size_t)nP * fs, cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaStreamSynchronize(st));

@@ -424,6 +424,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 struct MeTiledState {
     PFN_encodeTiled encode = nullptr;
+    // 0: persistent CTAs, one wave (one launch per clip).  k > 0: ceil(tiles / k) CTAs of ~k tiles each, so that the
+    // CTA scheduler can start the next launch (or a higher-priority kernel) on SMs as they free up: the pipelined
+    // host path, whose launches would otherwise each waste their last partial wave.
+    int tiles_per_cta = 0;
     bool attr_set[2][3][2] = {{{false}}};
     int occupancy[2][3][2] = {{{0}}};
 };
@@ -482,6 +486,10 @@ int me_tiled_run(MeTiledState &st, cudaStream_t stream, const MeGeom &g, const F
     a.npairs = npairs; a.ppg = fa.ppg; a.p_off = fa.p_off; a.zero = 0; a.mv = mv; a.cost = cost; a.flags = flags;
     const long long ntiles = (long long)a.tiles_x * a.tiles_y * npairs;
     long long grid = (long long)sm_count * st.occupancy[bi][ni][METRIC];
+    if (st.tiles_per_cta > 0) {
+        const long long g2 = (ntiles + st.tiles_per_cta - 1) / st.tiles_per_cta;
+        if (g2 > grid) grid = g2;
+    }
     if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, C::THREADS, C::SMEM, stream>>>(tm_ref, tm_cur, a);
     cudaError_t e = cudaGetLastError();

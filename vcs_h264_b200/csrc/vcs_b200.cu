@@ -42,6 +42,8 @@ struct vcs_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_aux = nullptr;
+    cudaStream_t s_search = nullptr, s_dct = nullptr;   // host pipeline: low-priority searches, high-priority DCT/pack
+    std::vector<cudaEvent_t> me_events;
     char err[512] = {0};
     double h_Q[192];
     double *d_Q = nullptr;
@@ -90,7 +92,11 @@ struct DevGuard {
 // the next call on the context (or vcs_synchronize) reports it once.
 int pending_device_error(vcs_ctx *ctx) {
     if (ctx->h_errflag && *(volatile int *)ctx->h_errflag) {
+        const int what = *(volatile int *)ctx->h_errflag;
         *(volatile int *)ctx->h_errflag = 0;
+        if (what == 2)
+            return fail(ctx, VCS_E_INVALID, "an earlier launch met a packed coefficient stream shorter than its bitmaps "
+                                            "claim (the affected blocks were decoded as zero)");
         return fail(ctx, VCS_E_INVALID, "an earlier launch met a motion vector pointing outside the frame "
                                         "(the prediction was zero-filled there)");
     }
@@ -264,14 +270,22 @@ EvTriple *next_events(vcs_ctx *ctx) {
 }
 
 // ME + residual/DCT/recon for nP P-frames addressed by fa, on stream st.
+// ME (+ residual/DCT/quant [+ recon]) of nP P-frames.  st2/ev_me: when given, the DCT stage runs on st2 after ev_me,
+// which is recorded on st behind the search (the pipelined host path keeps the next search off the DCT's critical path).
 int encode_dev(vcs_ctx *ctx, cudaStream_t st, const vcs_me_params *p, const FrameAddr &fa, int nP,
                int coef_mode, int16_t *mv, uint32_t *cost, uint8_t *flags, void *coef, uint8_t *recon,
-               unsigned long long *bitmap = nullptr, uint8_t *blk_esc = nullptr, uint2 *row_count = nullptr) {
+               unsigned long long *bitmap = nullptr, uint8_t *blk_esc = nullptr, uint2 *row_count = nullptr,
+               cudaStream_t st2 = nullptr, cudaEvent_t ev_me = nullptr) {
     EvTriple *ev = next_events(ctx);
     if (ev) CK(ctx, cudaEventRecord(ev->e0, st));
     int rc = launch_me(ctx, st, p, fa, nP, mv, cost, flags);
     if (rc) return rc;
     if (ev) { CK(ctx, cudaEventRecord(ev->e1, st)); ev->has_me = true; }
+    if (st2) {
+        CK(ctx, cudaEventRecord(ev_me, st));
+        CK(ctx, cudaStreamWaitEvent(st2, ev_me, 0));
+        st = st2;
+    }
     if (coef || recon) {
         DctArgs a;
         memset(&a, 0, sizeof(a));
@@ -286,7 +300,7 @@ int encode_dev(vcs_ctx *ctx, cudaStream_t st, const vcs_me_params *p, const Fram
         }
         rc = launch_dct(ctx, st, a, nP);
         if (rc) return rc;
-        if (ev) { CK(ctx, cudaEventRecord(ev->e2, st)); ev->has_dct = true; }
+        if (ev && !st2) { CK(ctx, cudaEventRecord(ev->e2, st)); ev->has_dct = true; }
     }
     return VCS_OK;
 }
@@ -486,10 +500,14 @@ int vcs_create(int device, vcs_ctx **out) {
     vcs_dct_matrix(C);
     static_assert(DCT_SMEM_BYTES <= 48 * 1024, "dct_stage_kernel relies on the default shared-memory limit");
     vcs_q_tables(50.0, ctx->h_Q);  // DCTcompressor.py:29 QF = 50
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->s_search, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->s_dct, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaMalloc(&ctx->d_Q, sizeof(ctx->h_Q)) != cudaSuccess ||
         cudaHostAlloc((void **)&ctx->h_errflag, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaMemcpyToSymbol(c_dct, C, sizeof(C)) != cudaSuccess ||
@@ -520,6 +538,9 @@ int vcs_destroy(vcs_ctx *ctx) {
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->s_aux) cudaStreamDestroy(ctx->s_aux);
+    if (ctx->s_search) cudaStreamDestroy(ctx->s_search);
+    if (ctx->s_dct) cudaStreamDestroy(ctx->s_dct);
+    for (auto &e : ctx->me_events) cudaEventDestroy(e);
     delete ctx;
     return VCS_OK;
 }
@@ -537,7 +558,9 @@ int vcs_use_own_stream(vcs_ctx *ctx) {
 }
 
 int vcs_synchronize(vcs_ctx *ctx) {
-    VCS_ENTER(ctx);
+    if (!ctx) return VCS_E_INVALID;
+    DevGuard guard(ctx->device);
+    // first wait, then look at the device's error flag: a kernel that is still running may raise it again
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return pending_device_error(ctx);
 }
@@ -933,7 +956,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
             ctx->seg_events.push_back(e);
         }
         if ((rc = packed_scratch(ctx, (size_t)nP * rows_per_p, p->W, (size_t)nP * npix * 3, nsegs, pd))) return rc;
-        CK(ctx, cudaMemsetAsync(pd.totals, 0, 16, ctx->stream));
+        CK(ctx, cudaMemsetAsync(pd.totals, 0, 16, ctx->stream));   // ordered before the pipeline's streams (see below)
         pk->lengths[0] = pk->lengths[1] = 0;
     }
     while ((int)ctx->chunk_events.size() < 2 * nsegs) {
@@ -949,7 +972,31 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
     if (trace) { cudaStreamSynchronize(ctx->stream); tmark(ctx->stream); cudaStreamWaitEvent(ctx->s_h2d, tev[0], 0); cudaStreamWaitEvent(ctx->s_d2h, tev[0], 0); }
     // (Running consecutive searches on two streams so that one fills the other's tail was tried and is slower:
     // the persistent search CTAs of the next chunk then keep the DCT stage of this chunk off the SMs.)
-    cudaStream_t sc = ctx->stream;
+    // Two compute streams: searches back to back on a low-priority one, each segment's DCT stage and packing on a
+    // high-priority one behind its search.  The search CTAs own a few tiles each instead of being persistent
+    // (VCS_TILES_PER_CTA, default 4; 0 = the single-stream schedule with persistent CTAs), so the next search fills the
+    // SMs the current one's last wave leaves idle, and a DCT stage that becomes ready is not kept waiting by a
+    // persistent grid.
+    int tiles_per_cta = 4;
+    if (const char *e = getenv("VCS_TILES_PER_CTA")) tiles_per_cta = atoi(e);
+    const bool two_streams = tiles_per_cta > 0;
+    cudaStream_t sc = two_streams ? ctx->s_search : ctx->stream;
+    cudaStream_t sd = two_streams ? ctx->s_dct : ctx->stream;
+    while (two_streams && (int)ctx->me_events.size() < nsegs) {
+        cudaEvent_t e;
+        CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->me_events.push_back(e);
+    }
+    struct TilesGuard {          // the device-resident entry points keep persistent CTAs
+        MeTiledState &st; int saved;
+        TilesGuard(MeTiledState &s, int k) : st(s), saved(s.tiles_per_cta) { st.tiles_per_cta = k; }
+        ~TilesGuard() { st.tiles_per_cta = saved; }
+    } tiles_guard(ctx->tiled, two_streams ? tiles_per_cta : 0);
+    if (two_streams) {           // work queued on the context's stream before this call comes first
+        CK(ctx, cudaEventRecord(ctx->chunk_events[0], ctx->stream));
+        CK(ctx, cudaStreamWaitEvent(sc, ctx->chunk_events[0], 0));
+        CK(ctx, cudaStreamWaitEvent(sd, ctx->chunk_events[0], 0));
+    }
     // Pass 1 queues everything that does not depend on what the host knows: uploads, kernels and -- without the packed
     // sink -- the downloads.  With the packed sink the size of a segment's value stream is only known once its scan
     // kernel has run, so each segment just sends that length (8 bytes, own stream: it must not queue behind the
@@ -993,14 +1040,15 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
                             d_rec ? d_rec + (size_t)p0 * fs : nullptr,
                             pk ? pd.bitmap + (size_t)p0 * rows_per_p * nbx8 : nullptr,
                             pk ? pd.blk_esc + (size_t)p0 * rows_per_p * nbx8 : nullptr,
-                            pk ? pd.row_count + (size_t)p0 * rows_per_p : nullptr);
+                            pk ? pd.row_count + (size_t)p0 * rows_per_p : nullptr,
+                            two_streams ? sd : nullptr, two_streams ? ctx->me_events[c] : nullptr);
             if (rc) return rc;
-            if (pk && (rc = launch_pack(ctx, sc, p->H, p->W, np, (const int8_t *)d_coef + (size_t)p0 * npix * 3, pd,
+            if (pk && (rc = launch_pack(ctx, sd, p->H, p->W, np, (const int8_t *)d_coef + (size_t)p0 * npix * 3, pd,
                                         (size_t)p0 * rows_per_p, pd.totals + 2 + 2 * c, d_rec == nullptr)))
                 return rc;
         }
-        CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sc));
-        tmark(sc);           // 3 + 4c: compute of segment c done
+        CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sd));
+        tmark(sd);           // 3 + 4c: compute of segment c done
         if (pk) {
             CK(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->chunk_events[2 * c + 1], 0));
             CK(ctx, cudaMemcpyAsync(&ctx->h_segend[2 * c], pd.totals + 2 + 2 * c, 16, cudaMemcpyDeviceToHost, ctx->s_aux));
@@ -1043,7 +1091,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
     rc = pipeline();
     // success or not, nothing may still be reading or writing the caller's buffers when this returns
     cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(sc), e3 = cudaStreamSynchronize(ctx->s_d2h),
-                e4 = cudaStreamSynchronize(ctx->s_aux);
+                e4 = cudaStreamSynchronize(ctx->s_aux), e5 = cudaStreamSynchronize(sd);
     if (trace && !tev.empty()) {
         auto ms = [&](size_t k) { float t = 0; cudaEventElapsedTime(&t, tev[0], tev[k]); return t; };
         fprintf(stderr, "[vcs trace] %d segments, %s sink; per segment: P-frames | upload done, compute start, compute done, download done (ms)\n",
@@ -1057,7 +1105,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
         for (auto e : tev) cudaEventDestroy(e);
     }
     if (rc) return rc;
-    CK(ctx, e1); CK(ctx, e2); CK(ctx, e3); CK(ctx, e4);
+    CK(ctx, e1); CK(ctx, e2); CK(ctx, e3); CK(ctx, e4); CK(ctx, e5);
     return pending_device_error(ctx);
 }
 

@@ -102,7 +102,7 @@ __device__ __forceinline__ uint32_t byte_of(const uint32_t *w, int k) { return (
 enum { DCT_FWD = 0, DCT_FWD_INV = 1, DCT_FWD_INV_NOCOEF = 2, DCT_INV = 3 };
 
 template <int CM, int PATH>
-__global__ void __launch_bounds__(DCT_THREADS, DCT_NCH == 1 ? 6 : 4)
+__global__ void __launch_bounds__(DCT_THREADS, DCT_NCH == 1 ? (PATH == DCT_FWD ? 8 : 6) : 4)
 dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     constexpr bool forward = PATH != DCT_INV, do_inverse = PATH != DCT_FWD, has_coef = PATH != DCT_FWD_INV_NOCOEF;
     constexpr int coef_mode = CM;

@@ -972,12 +972,13 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
     if (trace) { cudaStreamSynchronize(ctx->stream); tmark(ctx->stream); cudaStreamWaitEvent(ctx->s_h2d, tev[0], 0); cudaStreamWaitEvent(ctx->s_d2h, tev[0], 0); }
     // (Running consecutive searches on two streams so that one fills the other's tail was tried and is slower:
     // the persistent search CTAs of the next chunk then keep the DCT stage of this chunk off the SMs.)
-    // Two compute streams: searches back to back on a low-priority one, each segment's DCT stage and packing on a
-    // high-priority one behind its search.  The search CTAs own a few tiles each instead of being persistent
-    // (VCS_TILES_PER_CTA, default 4; 0 = the single-stream schedule with persistent CTAs), so the next search fills the
-    // SMs the current one's last wave leaves idle, and a DCT stage that becomes ready is not kept waiting by a
-    // persistent grid.
-    int tiles_per_cta = 4;
+    // Optional two-stream schedule (VCS_TILES_PER_CTA=k > 0): searches back to back on a low-priority stream with k
+    // tiles per CTA instead of persistent CTAs, each segment's DCT stage and packing on a high-priority stream behind
+    // its search, so that the next search fills the SMs the current one's last wave leaves idle.  Measured slower than
+    // the default single stream with persistent CTAs (k = 1/2/4/8: 10.98/11.21/11.59/11.91 ms against 10.95 ms dense):
+    // a DCT stage that becomes ready has to wait for running search CTAs to retire, and CTAs that own few tiles lose
+    // the cross-tile TMA prefetch.
+    int tiles_per_cta = 0;
     if (const char *e = getenv("VCS_TILES_PER_CTA")) tiles_per_cta = atoi(e);
     const bool two_streams = tiles_per_cta > 0;
     cudaStream_t sc = two_streams ? ctx->s_search : ctx->stream;

@@ -89,7 +89,6 @@ struct TiledArgs {
     int zchunk;                // index (cy*ncx+cx) of the chunk holding offset (0,0), or 0
     int npairs, ppg, p_off;
     uint32_t zero;             // always 0; opaque to the compiler (pipe balancing, see the wrap8 loop)
-    unsigned int *tile_counter;   // zeroed before the launch: CTAs take tiles from it in (P-frame, raster) order
     int16_t *mv;
     uint32_t *cost;
     uint8_t *flags;
@@ -157,21 +156,14 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     const int nch = a.ncy * a.ncx;
     const int tiles_per_pair = a.tiles_x * a.tiles_y;
     const long long ntiles = (long long)tiles_per_pair * a.npairs;
-    // Tiles are handed out dynamically (one atomicAdd per tile) in (P-frame, raster) order: every CTA stays busy
-    // until the queue is empty -- with a static stride the launch ends with its unluckiest CTA -- and the cheap
-    // bottom-row tiles of the last frame come last.  sTile is a ring of the tiles this CTA holds: thread 0 takes tile
-    // q when it issues the TMA loads of its first unit, two units ahead of the search, so the entry is visible to
-    // everybody (a __syncthreads later) long before unit s = q * nch reads it.
-    long long *sTile = reinterpret_cast<long long *>(sBar + 2);   // 4 entries behind the two barriers (SZ_MISC keeps 64 bytes)
-    auto take_tile = [&](long long q) {            // thread 0 only
-        const long long t = (long long)atomicAdd(a.tile_counter, 1u);
-        sTile[q & 3] = t < ntiles ? t : -1;
-    };
+    // tiles of this CTA: blockIdx.x, +gridDim.x, ...
+    const long long my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_units = my_tiles * nch;
+    if (n_units == 0) return;
 
-    // geometry of work unit s of this CTA; false when the queue ran dry before its tile
-    auto unit_geom = [&](long long s, int &p, int &tx, int &ty, int &cy, int &cx, bool &first, bool &last) -> bool {
-        const long long tile = sTile[(s / nch) & 3];
-        if (tile < 0) return false;
+    // geometry of work unit s of this CTA
+    auto unit_geom = [&](long long s, int &p, int &tx, int &ty, int &cy, int &cx, bool &first, bool &last) {
+        const long long tile = blockIdx.x + (s / nch) * gridDim.x;
         const int c = (int)(s % nch);
         const int cc = (c + a.zchunk) % nch;          // the chunk holding offset (0,0) goes first
         first = c == 0;
@@ -182,12 +174,10 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
         tx = t - ty * a.tiles_x;
         cy = cc / a.ncx;
         cx = cc - cy * a.ncx;
-        return true;
     };
-    auto issue = [&](long long s) {   // one elected thread: take the tile if s opens one, arm the barrier, start both TMA loads
-        if (s % nch == 0) take_tile(s / nch);
+    auto issue = [&](long long s) {   // one elected thread: arm the barrier, start both TMA loads
         int p, tx, ty, cy, cx; bool f, l;
-        if (!unit_geom(s, p, tx, ty, cy, cx, f, l)) return;
+        unit_geom(s, p, tx, ty, cy, cx, f, l);
         const int b = (int)(s & 1);
         const int xw0 = tx * MX * BS + a.lo + cx * ND, yw0 = ty * C::MY * BS + a.lo + cy * ND;
         mbar_expect_tx(&sBar[b], (uint32_t)(C::RAWW * C::WR * 4 + C::CURW * C::CURR * 4));
@@ -203,11 +193,12 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
         mbar_init(&sBar[0], 1);
         mbar_init(&sBar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sTile[0] = sTile[1] = sTile[2] = sTile[3] = -1;
-        issue(0);
-        issue(1);
     }
     __syncthreads();
+    if (tid == 0) {
+        issue(0);
+        if (n_units > 1) issue(1);
+    }
 
     // per-thread role in the search: (macroblock, dx index inside the chunk).  A quarter-warp that straddles two
     // macroblocks breaks the 3*dx bank rotation of its LDS.128 (2-way conflict), so when ND = 32k + 1 warp m takes
@@ -224,9 +215,9 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     const int mbx = mb % MX, mby = mb / MX;
     const bool has_item = WARP_PER_MB ? tid < 33 * NMB : tid < C::ITEMS;
 
-    for (long long s = 0;; ++s) {
+    for (long long s = 0; s < n_units; ++s) {
         int p, tx, ty, cy, cx; bool first, last;
-        if (!unit_geom(s, p, tx, ty, cy, cx, first, last)) break;     // CTA-uniform: the queue is empty
+        unit_geom(s, p, tx, ty, cy, cx, first, last);
         const int b = (int)(s & 1);
         const int xw0 = tx * MX * BS + a.lo + cx * ND, yw0 = ty * C::MY * BS + a.lo + cy * ND;
         const int ao = 3 * xw0 - 16 * floordiv16(3 * xw0);   // byte offset of the window inside a raw row
@@ -281,7 +272,7 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
             }
         }
         __syncthreads();   // T, curT ready; raw stage b is free again
-        if (tid == 0) {
+        if (tid == 0 && s + 2 < n_units) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(s + 2);
         }
@@ -437,12 +428,11 @@ struct MeTiledState {
     // CTA scheduler can start the next launch (or a higher-priority kernel) on SMs as they free up: the pipelined
     // host path, whose launches would otherwise each waste their last partial wave.
     int tiles_per_cta = 0;
-    unsigned int *d_tile_counter = nullptr;   // the tile queue's head, zeroed in stream order before every launch
     bool attr_set[2][3][2] = {{{false}}};
     int occupancy[2][3][2] = {{{0}}};
 };
 
-inline void me_tiled_destroy(MeTiledState &st) { if (st.d_tile_counter) cudaFree(st.d_tile_counter); st.d_tile_counter = nullptr; }
+inline void me_tiled_destroy(MeTiledState &) {}
 
 template <class C, int METRIC>
 int me_tiled_run(MeTiledState &st, cudaStream_t stream, const MeGeom &g, const FrameAddr &fa, int npairs,
@@ -494,15 +484,6 @@ int me_tiled_run(MeTiledState &st, cudaStream_t stream, const MeGeom &g, const F
     a.zchunk = 0;
     if (g.lo <= 0 && g.hi >= 0) { const int cz = (-g.lo) / C::ND; a.zchunk = cz * a.ncx + cz; }
     a.npairs = npairs; a.ppg = fa.ppg; a.p_off = fa.p_off; a.zero = 0; a.mv = mv; a.cost = cost; a.flags = flags;
-    if (!st.d_tile_counter && cudaMalloc(&st.d_tile_counter, sizeof(unsigned int)) != cudaSuccess) {
-        snprintf(err, errlen, "cudaMalloc(tile counter) failed");
-        return -3;
-    }
-    if (cudaMemsetAsync(st.d_tile_counter, 0, sizeof(unsigned int), stream) != cudaSuccess) {
-        snprintf(err, errlen, "cudaMemsetAsync(tile counter) failed");
-        return -2;
-    }
-    a.tile_counter = st.d_tile_counter;
     const long long ntiles = (long long)a.tiles_x * a.tiles_y * npairs;
     long long grid = (long long)sm_count * st.occupancy[bi][ni][METRIC];
     if (st.tiles_per_cta > 0) {

@@ -261,14 +261,12 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
             }
             if (tid < NMB) {
                 if (first) { sBest[tid] = ~0ull; sStatic[tid] = 0; }
-                // valid dy of this chunk for macroblock row (tid / MX): inside [lo,hi] and inside the frame
-                const int y = (ty * C::MY + tid / MX) * BS;
-                unsigned long long m = 0;
-                for (int d = 0; d < ND; ++d) {
-                    const int off = a.lo + cy * ND + d, i = y + off;
-                    if (off <= a.hi && i >= 0 && i <= a.H - BS - a.slack) m |= 1ull << d;
-                }
-                sDyMask[tid] = m;
+                // valid dy of this chunk for macroblock row (tid / MX): offsets inside [lo,hi] whose row i = y + off lies
+                // inside the frame, 0 <= i <= H - BS - slack: one interval of d, so a mask in closed form
+                const int y = (ty * C::MY + tid / MX) * BS, off0 = a.lo + cy * ND;
+                const int d_lo = max(0, -(y + off0));
+                const int d_hi = min(ND - 1, min(a.hi - off0, a.H - BS - a.slack - y - off0));
+                sDyMask[tid] = d_hi >= d_lo ? ((~0ull >> (63 - d_hi)) & (~0ull << d_lo)) : 0ull;
             }
         }
         __syncthreads();   // T, curT ready; raw stage b is free again

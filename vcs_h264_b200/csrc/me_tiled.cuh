@@ -45,8 +45,10 @@ template <int BS_, int ND_>
 struct TiledCfg {
     static constexpr int BS = BS_;            // macroblock size (8 or 16)
     static constexpr int ND = ND_;            // offsets per chunk and axis (9, 17 or 33)
-    static constexpr int MX = ND_ == 9 ? 7 : 5;   // macroblocks per tile, x
-    static constexpr int MY = ND_ == 9 ? 2 : 3;   // macroblocks per tile, y
+    // macroblocks per tile: the more offsets a thread set covers, the fewer macroblocks fill the CTA.  Small ranges get
+    // larger tiles (the window overhead (tile + ND)^2 / tile^2 shrinks and the CTA keeps 8-12 warps instead of 4-8).
+    static constexpr int MX = ND_ == 33 ? 5 : 7;              // x
+    static constexpr int MY = ND_ == 33 ? 3 : (ND_ == 17 ? 3 : 4);   // y
     static constexpr int NMB = MX * MY;
     static constexpr int ITEMS = NMB * ND;    // (macroblock, dx) pairs
     static constexpr int THREADS = (ITEMS + 127) / 128 * 128;
@@ -70,10 +72,12 @@ struct TiledCfg {
     static constexpr size_t OFF_RAW = (OFF_T + SZ_T + 127) / 128 * 128;
     static constexpr size_t SZ_RAW = (size_t)(RAWW * WR + 4) * 4;     // +4: funnel read past the end
     static constexpr size_t SZ_RAW_AL = (SZ_RAW + 127) / 128 * 128;
-    static constexpr size_t OFF_CRAW = OFF_RAW + 2 * SZ_RAW_AL;
+    // ONE raw stage: it is free again as soon as the window has been re-laid, i.e. for the whole search of the unit,
+    // which is when the next unit's TMA loads land in it
+    static constexpr size_t OFF_CRAW = OFF_RAW + SZ_RAW_AL;
     static constexpr size_t SZ_CRAW = (size_t)CURW * CURR * 4;
     static constexpr size_t SZ_CRAW_AL = (SZ_CRAW + 127) / 128 * 128;
-    static constexpr size_t OFF_CURT = OFF_CRAW + 2 * SZ_CRAW_AL;
+    static constexpr size_t OFF_CURT = OFF_CRAW + SZ_CRAW_AL;
     static constexpr size_t SZ_CURT = (size_t)NMB * WPR * BS * 4;      // [mb][w][v]
     static constexpr size_t OFF_MISC = (OFF_CURT + 2 * SZ_CURT + 127) / 128 * 128;  // 2: wrap8 L/H
     static constexpr size_t SZ_MISC = 8 * NMB + 8 * NMB + 4 * NMB + 4 * NMB + 64;
@@ -178,27 +182,21 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     auto issue = [&](long long s) {   // one elected thread: arm the barrier, start both TMA loads
         int p, tx, ty, cy, cx; bool f, l;
         unit_geom(s, p, tx, ty, cy, cx, f, l);
-        const int b = (int)(s & 1);
         const int xw0 = tx * MX * BS + a.lo + cx * ND, yw0 = ty * C::MY * BS + a.lo + cy * ND;
-        mbar_expect_tx(&sBar[b], (uint32_t)(C::RAWW * C::WR * 4 + C::CURW * C::CURR * 4));
+        mbar_expect_tx(&sBar[0], (uint32_t)(C::RAWW * C::WR * 4 + C::CURW * C::CURR * 4));
         // the innermost TMA coordinate must land on a 16-byte boundary: align down, keep the remainder
         const int pg = p + a.p_off;   // launches may start inside a GOP
-        tma_load_3d(smem + C::OFF_RAW + b * C::SZ_RAW_AL, &tm_ref, &sBar[b], 4 * floordiv16(3 * xw0), yw0,
+        tma_load_3d(smem + C::OFF_RAW, &tm_ref, &sBar[0], 4 * floordiv16(3 * xw0), yw0, pg / a.ppg);
+        tma_load_4d(smem + C::OFF_CRAW, &tm_cur, &sBar[0], 4 * floordiv16(tx * MX * BS * 3), ty * C::MY * BS, pg % a.ppg,
                     pg / a.ppg);
-        tma_load_4d(smem + C::OFF_CRAW + b * C::SZ_CRAW_AL, &tm_cur, &sBar[b], 4 * floordiv16(tx * MX * BS * 3),
-                    ty * C::MY * BS, pg % a.ppg, pg / a.ppg);
     };
 
     if (tid == 0) {
         mbar_init(&sBar[0], 1);
-        mbar_init(&sBar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
-        issue(0);
-        if (n_units > 1) issue(1);
-    }
+    if (tid == 0) issue(0);
 
     // per-thread role in the search: (macroblock, dx index inside the chunk).  A quarter-warp that straddles two
     // macroblocks breaks the 3*dx bank rotation of its LDS.128 (2-way conflict), so when ND = 32k + 1 warp m takes
@@ -218,15 +216,14 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     for (long long s = 0; s < n_units; ++s) {
         int p, tx, ty, cy, cx; bool first, last;
         unit_geom(s, p, tx, ty, cy, cx, first, last);
-        const int b = (int)(s & 1);
-        const int xw0 = tx * MX * BS + a.lo + cx * ND, yw0 = ty * C::MY * BS + a.lo + cy * ND;
+        const int xw0 = tx * MX * BS + a.lo + cx * ND;
         const int ao = 3 * xw0 - 16 * floordiv16(3 * xw0);   // byte offset of the window inside a raw row
         const int cao = (tx * MX * BS * 3 - 16 * floordiv16(tx * MX * BS * 3)) >> 2;   // word offset of the MB tile
-        mbar_wait(&sBar[b], (uint32_t)((s >> 1) & 1));
+        mbar_wait(&sBar[0], (uint32_t)(s & 1));
 
         // ---- re-lay the raw window: 4 byte phases, transposed [phase][word col][row] ----------
         {
-            const uint32_t *raw = reinterpret_cast<const uint32_t *>(smem + C::OFF_RAW + b * C::SZ_RAW_AL);
+            const uint32_t *raw = reinterpret_cast<const uint32_t *>(smem + C::OFF_RAW);
             constexpr int RG = (C::WR + 31) / 32, JQ = (C::NC + 3) / 4;   // row groups x column quads
             for (int task = warp; task < RG * JQ; task += C::THREADS / 32) {
                 const int rg = task / JQ, jq = task - rg * JQ;
@@ -250,7 +247,7 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
                 }
             }
             // macroblocks: raw [row][word] -> [mb][w][v]
-            const uint32_t *craw = reinterpret_cast<const uint32_t *>(smem + C::OFF_CRAW + b * C::SZ_CRAW_AL);
+            const uint32_t *craw = reinterpret_cast<const uint32_t *>(smem + C::OFF_CRAW);
             // lanes run along v (rows): conflict-free stores; a row pitch of CURW words with CURW/4 odd
             // keeps the strided reads at <= 2-way
             for (int k = tid; k < NMB * WPR * BS; k += C::THREADS) {
@@ -269,10 +266,10 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
                 sDyMask[tid] = d_hi >= d_lo ? ((~0ull >> (63 - d_hi)) & (~0ull << d_lo)) : 0ull;
             }
         }
-        __syncthreads();   // T, curT ready; raw stage b is free again
-        if (tid == 0 && s + 2 < n_units) {
+        __syncthreads();   // T, curT ready; the raw stage is free again: the next unit's loads overlap this unit's search
+        if (tid == 0 && s + 1 < n_units) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(s + 2);
+            issue(s + 1);
         }
 
         // ---- static test (motion.py:109-116), on the chunk that holds offset (0,0) ------------

@@ -25,7 +25,7 @@ def main():
     import vcs_h264_b200 as v
     from vcs_h264_b200 import synth
     ap = argparse.ArgumentParser()
-    ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--frames", type=int, default=24)
     ap.add_argument("--metric", default="sad", choices=["wrap8", "sad"])
     ap.add_argument("--iters", type=int, default=5)
     args = ap.parse_args()

@@ -159,27 +159,30 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nch = a.ncy * a.ncx;
     const int tiles_per_pair = a.tiles_x * a.tiles_y;
-    const long long ntiles = (long long)tiles_per_pair * a.npairs;
+    const int ntiles = tiles_per_pair * a.npairs;        // < 2^31 (checked on the host)
     // tiles of this CTA: blockIdx.x, +gridDim.x, ...
-    const long long my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const long long n_units = my_tiles * nch;
+    const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_units = my_tiles * nch;
     if (n_units == 0) return;
 
-    // geometry of work unit s of this CTA
-    auto unit_geom = [&](long long s, int &p, int &tx, int &ty, int &cy, int &cx, bool &first, bool &last) {
-        const long long tile = blockIdx.x + (s / nch) * gridDim.x;
-        const int c = (int)(s % nch);
-        const int cc = (c + a.zchunk) % nch;          // the chunk holding offset (0,0) goes first
+    // geometry of work unit s of this CTA.  32-bit arithmetic only: this runs in every thread for every unit, and the
+    // 64-bit divisions it used to make were a third of the instructions outside the inner loop.
+    auto unit_geom = [&](int s, int &p, int &tx, int &ty, int &cy, int &cx, bool &first, bool &last) {
+        const unsigned q = nch == 1 ? (unsigned)s : (unsigned)s / (unsigned)nch;
+        const int c = nch == 1 ? 0 : s - (int)q * nch;
+        const unsigned tile = blockIdx.x + q * gridDim.x;
+        int cc = c + a.zchunk;                         // the chunk holding offset (0,0) goes first
+        if (cc >= nch) cc -= nch;
         first = c == 0;
         last = c == nch - 1;
-        p = (int)(tile / tiles_per_pair);
-        const int t = (int)(tile - (long long)p * tiles_per_pair);
-        ty = t / a.tiles_x;
-        tx = t - ty * a.tiles_x;
-        cy = cc / a.ncx;
+        p = (int)(tile / (unsigned)tiles_per_pair);
+        const unsigned t = tile - (unsigned)p * (unsigned)tiles_per_pair;
+        ty = (int)(t / (unsigned)a.tiles_x);
+        tx = (int)t - ty * a.tiles_x;
+        cy = nch == 1 ? 0 : cc / a.ncx;
         cx = cc - cy * a.ncx;
     };
-    auto issue = [&](long long s) {   // one elected thread: arm the barrier, start both TMA loads
+    auto issue = [&](int s) {   // one elected thread: arm the barrier, start both TMA loads
         int p, tx, ty, cy, cx; bool f, l;
         unit_geom(s, p, tx, ty, cy, cx, f, l);
         const int xw0 = tx * MX * BS + a.lo + cx * ND, yw0 = ty * C::MY * BS + a.lo + cy * ND;
@@ -213,7 +216,7 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     const int mbx = mb % MX, mby = mb / MX;
     const bool has_item = WARP_PER_MB ? tid < 33 * NMB : tid < C::ITEMS;
 
-    for (long long s = 0; s < n_units; ++s) {
+    for (int s = 0; s < n_units; ++s) {
         int p, tx, ty, cy, cx; bool first, last;
         unit_geom(s, p, tx, ty, cy, cx, first, last);
         const int xw0 = tx * MX * BS + a.lo + cx * ND;
@@ -377,10 +380,15 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
             // multiply-add runs on the FMA pipe, only the min and the validity select use the busy ALU pipe.
             static_assert(ND <= 64 && 255 * 3 * BS * BS < (1 << 26), "32-bit key layout");
             uint32_t k32 = 0xFFFFFFFFu;
+            if (dymask == (~0ull >> (64 - ND))) {        // interior rows: every dy is valid (the common case)
 #pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                const uint32_t k = ((dymask >> d) & 1) ? acc[d] * 64u + (uint32_t)d : 0xFFFFFFFFu;
-                k32 = min(k32, k);
+                for (int d = 0; d < ND; ++d) k32 = min(k32, acc[d] * 64u + (uint32_t)d);
+            } else {
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    const uint32_t k = ((dymask >> d) & 1) ? acc[d] * 64u + (uint32_t)d : 0xFFFFFFFFu;
+                    k32 = min(k32, k);
+                }
             }
             unsigned long long best = ~0ull;
             if (k32 != 0xFFFFFFFFu)
@@ -480,6 +488,7 @@ int me_tiled_run(MeTiledState &st, cudaStream_t stream, const MeGeom &g, const F
     if (g.lo <= 0 && g.hi >= 0) { const int cz = (-g.lo) / C::ND; a.zchunk = cz * a.ncx + cz; }
     a.npairs = npairs; a.ppg = fa.ppg; a.p_off = fa.p_off; a.zero = 0; a.mv = mv; a.cost = cost; a.flags = flags;
     const long long ntiles = (long long)a.tiles_x * a.tiles_y * npairs;
+    if (ntiles * a.ncy * a.ncx >= (1ll << 31)) { snprintf(err, errlen, "too many work units in one launch (%lld tiles)", ntiles); return -1; }
     long long grid = (long long)sm_count * st.occupancy[bi][ni][METRIC];
     if (st.tiles_per_cta > 0) {
         const long long g2 = (ntiles + st.tiles_per_cta - 1) / st.tiles_per_cta;

@@ -30,11 +30,11 @@
 #include "common.cuh"
 
 // wrap8 loop: the subtracts of the offsets d with bit (d mod VCS_WRAP_ALU_DEN) set in VCS_WRAP_ALU_MASK are forced onto
-// the ALU pipe (IADD3), the rest go to the FMA pipe (IMAD.IADD); 2 of 5 measured best, and among the ten 2-of-5 masks
-// 0x6 (9.14 ms per 45 P-frames; the others 9.18-9.24: same instruction mix, different ptxas schedule) (tools/ab_me.sh builds and
-// times other splits).
+// the ALU pipe (IADD3), the rest go to the FMA pipe (IMAD.IADD).  Round-2 A/B of 18 splits on one B200 (tools/ab_me.sh +
+// tools/ab_run.sh, two runs each, 45 P-frames): 0xa/5 9.02 ms, 0x9/5 9.05, 0x29/8 9.06, 0x6/5 9.10, ... 0x1/2 9.24 -- the
+// instruction mix is the same for equal ratios, only the ptxas schedule differs.
 #ifndef VCS_WRAP_ALU_MASK
-#define VCS_WRAP_ALU_MASK 0x6
+#define VCS_WRAP_ALU_MASK 0xa
 #define VCS_WRAP_ALU_DEN 5
 #endif
 
@@ -316,6 +316,9 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
             const uint32_t *col = sT + (sb & 3) * PS + (sb >> 2) * RP + BS * mby;
             const uint32_t *cl = sCurT + mb * WPR * BS;
             const uint32_t *ch = sCurH + mb * WPR * BS;
+            // wrap8 accumulates 64 * byte-sum (IDP.4A with every multiplier byte = 64), so that the argmin key
+            // cost * 64 + d below needs no shift; SAD (VABSDIFF4.ACC adds plain bytes) scales at the end.
+            constexpr uint32_t WRAP_MUL = 0x40404040u, KEY_MUL = METRIC == 0 ? 1u : 64u;
             uint32_t acc[ND];
 #pragma unroll
             for (int d = 0; d < ND; ++d) acc[d] = 0;
@@ -361,7 +364,7 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
                                                 : "=r"(z) : "r"(r1), "r"(c[v]), "r"(r2), "r"(chh[v]), "r"(zero));
                                         else
                                             asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(z) : "r"(r1 - c[v]), "r"(r2), "r"(chh[v]));
-                                        acc[d] = __dp4a(z, 0x01010101u, acc[d]);
+                                        acc[d] = __dp4a(z, WRAP_MUL, acc[d]);
                                     }
                                 }
                             } else {
@@ -376,17 +379,17 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
                 }
             }
             // first strict minimum in scan order.  Within the thread dx is fixed, so (cost, dy) decides:
-            // a 32-bit key cost*64 + d (cost < 2^18 for bs <= 16, d < 64) reduced with integer min; the
-            // multiply-add runs on the FMA pipe, only the min and the validity select use the busy ALU pipe.
+            // a 32-bit key cost*64 + d (cost < 2^18 for bs <= 16, d < 64) reduced with integer min.  wrap8 sums already
+            // carry the factor 64, so a key is one fused add+min (VIADDMNMX); SAD sums are scaled here (LEA).
             static_assert(ND <= 64 && 255 * 3 * BS * BS < (1 << 26), "32-bit key layout");
             uint32_t k32 = 0xFFFFFFFFu;
             if (dymask == (~0ull >> (64 - ND))) {        // interior rows: every dy is valid (the common case)
 #pragma unroll
-                for (int d = 0; d < ND; ++d) k32 = min(k32, acc[d] * 64u + (uint32_t)d);
+                for (int d = 0; d < ND; ++d) k32 = min(k32, acc[d] * KEY_MUL + (uint32_t)d);
             } else {
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
-                    const uint32_t k = ((dymask >> d) & 1) ? acc[d] * 64u + (uint32_t)d : 0xFFFFFFFFu;
+                    const uint32_t k = ((dymask >> d) & 1) ? acc[d] * KEY_MUL + (uint32_t)d : 0xFFFFFFFFu;
                     k32 = min(k32, k);
                 }
             }

@@ -278,7 +278,7 @@ def ncu_traffic():
                     return None
         return None
     me = pick(lambda n: "me_" in n and re.search(r">,\s*0>", n) is not None)
-    dct = pick(lambda n: "dct_stage_kernel<3, 1>" in n)
+    dct = pick(lambda n: "dct_stage_kernel<3, 1" in n)
     return me, dct, os.path.basename(files[-1])
 
 

@@ -106,9 +106,10 @@ __device__ __forceinline__ int clip_u8(int v) { return min(max(v, 0), 255); }
 
 __device__ __forceinline__ void bgr2ycrcb(int B, int G, int R, int &Y, int &Cr, int &Cb) {
     const int half = 1 << 13;
+    // ranges over all 2^24 inputs: Y 0..255, Cr 0..256, Cb 1..255 -- only Cr can need the saturation
     Y = (1868 * B + 9617 * G + 4899 * R + half) >> 14;
-    Cr = clip_u8(((R - Y) * 11682 + (128 << 14) + half) >> 14);
-    Cb = clip_u8(((B - Y) * 9241 + (128 << 14) + half) >> 14);
+    Cr = min(((R - Y) * 11682 + (128 << 14) + half) >> 14, 255);
+    Cb = ((B - Y) * 9241 + (128 << 14) + half) >> 14;
 }
 
 __device__ __forceinline__ void ycrcb2bgr(int Y, int Cr, int Cb, int &B, int &G, int &R) {

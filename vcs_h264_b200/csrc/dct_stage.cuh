@@ -46,11 +46,14 @@ constexpr int DCT_TILE_W = 32;                        // pixels per warp tile ro
 constexpr int DCT_WARPS = 4;                          // warps per CTA, each with a private tile
 constexpr int DCT_NCH = 1;                            // channels per pass group (1 or 3)
 constexpr int DCT_THREADS = 32 * DCT_WARPS;
-constexpr int DCT_RS = DCT_TILE_W + 1;                // row stride of the double tiles: conflict-free
+constexpr int DCT_RS = DCT_TILE_W + 2;                // row stride of the double tiles: even, so a lane's 8 row values are 4 aligned
+                                                      // LDS.128, and (4i + 16 blk + 2k) mod 32 keeps column and row accesses conflict-free
+constexpr int DCT_QS = 10;                            // row stride of the Q tables [ch][i][QS]: 20 i mod 32 words, conflict-free LDS.128
+constexpr int DCT_QN = 3 * 8 * DCT_QS;                // doubles per table
 constexpr int DCT_X_DOUBLES = DCT_NCH * 8 * DCT_RS;   // per-warp transform tile [NCH][8][RS]
 constexpr int DCT_PLANE = 8 * DCT_TILE_W * 3;         // bytes of one 8 x 32 x 3 byte tile
 constexpr size_t DCT_WARP_BYTES = (size_t)DCT_X_DOUBLES * sizeof(double) + 3 * DCT_PLANE;
-constexpr size_t DCT_SMEM_BYTES = 2 * 192 * sizeof(double) + DCT_WARPS * DCT_WARP_BYTES;
+constexpr size_t DCT_SMEM_BYTES = 2 * DCT_QN * sizeof(double) + DCT_WARPS * DCT_WARP_BYTES;
 
 struct DctArgs {
     int H, W;
@@ -95,22 +98,47 @@ __device__ __forceinline__ void load24(const uint8_t *p, uint32_t w[6]) {
     for (int k = 0; k < 6; ++k) w[k] = sh ? __funnelshift_r(r[k], r[k + 1], sh) : r[k];
 }
 
-__device__ __forceinline__ uint32_t byte_of(const uint32_t *w, int k) { return (w[k >> 2] >> (8 * (k & 3))) & 0xffu; }
+// byte k of a word array, zero-extended: one PRMT (the shift-and-mask form costs two ALU instructions)
+__device__ __forceinline__ uint32_t byte_of(const uint32_t *w, int k) { return __byte_perm(w[k >> 2], 0u, 0x4440u | (uint32_t)(k & 3)); }
+// word with its byte `pos` replaced by the low byte of v.  Position 0 STARTS a word with v as it is: the callers fill
+// positions 0..3 in order, so whatever v carries above its low byte is overwritten by the next three calls.
+__device__ __forceinline__ uint32_t put_byte(uint32_t word, uint32_t v, int pos) {
+    return pos == 0 ? v : pos == 1 ? __byte_perm(word, v, 0x3240u)
+         : pos == 2 ? __byte_perm(word, v, 0x3410u) : __byte_perm(word, v, 0x4210u);
+}
+// the same for 16-bit halves (positions 0, 1)
+__device__ __forceinline__ uint32_t put_half(uint32_t word, uint32_t v, int pos) {
+    return pos == 0 ? v : __byte_perm(word, v, 0x5410u);
+}
 
 // Compile-time variants: CM = coefficient format (VCS_COEF_*), PATH = which halves run.  The quantiser sits in the
 // innermost loop, so run-time mode tests there cost more issue slots than the arithmetic they guard.
 enum { DCT_FWD = 0, DCT_FWD_INV = 1, DCT_FWD_INV_NOCOEF = 2, DCT_INV = 3 };
 
+#ifndef VCS_DCT_MINB_FWD
+#define VCS_DCT_MINB_FWD 7
+#endif
+#ifndef VCS_DCT_MINB
+#define VCS_DCT_MINB 7
+#endif
+// (A full-width specialisation that drops the partial-tile predicates was tried: without the branches ptxas merges the
+// stages into one block, hoists loads across them and spills -- 104 bytes of stack at 80 registers.  Not kept.)
 template <int CM, int PATH>
-__global__ void __launch_bounds__(DCT_THREADS, DCT_NCH == 1 ? (PATH == DCT_FWD ? 8 : 6) : 4)
+__global__ void __launch_bounds__(DCT_THREADS, DCT_NCH == 1 ? (PATH == DCT_FWD ? VCS_DCT_MINB_FWD : VCS_DCT_MINB) : 4)
 dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     constexpr bool forward = PATH != DCT_INV, do_inverse = PATH != DCT_FWD, has_coef = PATH != DCT_FWD_INV_NOCOEF;
     constexpr int coef_mode = CM;
     extern __shared__ __align__(16) unsigned char dct_smem[];
     double *s_q = reinterpret_cast<double *>(dct_smem);          // Q [3][64]
-    double *s_rq = s_q + 192;                                    // RN(1/Q)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *wbase = dct_smem + 2 * 192 * sizeof(double) + warp * DCT_WARP_BYTES;
+    double *s_rq = s_q + DCT_QN;                                 // RN(1/Q)
+    // lane and the warp's shared-memory offset are pinned in registers (the empty asm makes them opaque): ptxas otherwise
+    // re-derives them from %tid at every use, 19 S2R + 50 integer instructions per tile
+    int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t wofs = (uint32_t)(2 * DCT_QN * sizeof(double)) + (uint32_t)warp * (uint32_t)DCT_WARP_BYTES;
+    asm volatile("" : "+r"(lane));
+    asm volatile("" : "+r"(wofs));
+    unsigned char *wbase = dct_smem + wofs;
     double *s_x = reinterpret_cast<double *>(wbase);                              // [3][8][RS]
     uint8_t *s_pred = wbase + DCT_X_DOUBLES * sizeof(double);                     // [8][32*3] prediction (BGR)
     int8_t *s_in8 = reinterpret_cast<int8_t *>(s_pred + DCT_PLANE);               // [3][8][32] YCrCb-128
@@ -120,12 +148,12 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     const size_t npix = (size_t)H * W;
     const int N = nbx * nby;
 
-    // stored transposed, [ch][j][i]: in the row passes lanes differ in i, so they read consecutive doubles
+    // [ch][i][QS]: in the row passes a lane (block, row i) reads its 8 divisors as 4 aligned 16-byte words
     for (int k = threadIdx.x; k < 192; k += DCT_THREADS) {
         const double q = a.Q[k];
         const int ch = k >> 6, i = (k >> 3) & 7, j = k & 7;
-        s_q[ch * 64 + j * 8 + i] = q;
-        s_rq[ch * 64 + j * 8 + i] = 1.0 / q;
+        s_q[(ch * 8 + i) * DCT_QS + j] = q;
+        s_rq[(ch * 8 + i) * DCT_QS + j] = 1.0 / q;
     }
     __syncthreads();   // the only CTA-wide barrier
 
@@ -140,18 +168,34 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     const int rp_i = lane & 7, rp_blk = lane >> 3;          // row passes: row i of block blk
     const int rbase0 = rp_i * DCT_RS + rp_blk * 8;          // + ch * 8 * RS
 
-    for (unsigned item = blockIdx.x * DCT_WARPS + warp; item < nitems; item += nwarps) {
-        const unsigned pu = item / tiles_per_frame, rem = item - pu * tiles_per_frame, tyu = rem / (unsigned)ntx;
-        const int p = (int)pu, ty = (int)tyu, tx = (int)(rem - tyu * (unsigned)ntx);
+    // The warp walks items first, first + nwarps, ...: (p, ty, tx) advance by constant steps with two carries, and the
+    // frame pointers are refreshed only when p changes -- the divisions this replaces were 100 instructions per tile.
+    const unsigned first = blockIdx.x * DCT_WARPS + warp;
+    const unsigned step_p = nwarps / tiles_per_frame, step_r = nwarps - step_p * tiles_per_frame;
+    const int step_ty = (int)(step_r / (unsigned)ntx), step_tx = (int)(step_r - (unsigned)step_ty * (unsigned)ntx);
+    int p = (int)(first / tiles_per_frame), ty, tx;
+    {
+        const unsigned rem = first - (unsigned)p * tiles_per_frame;
+        ty = (int)(rem / (unsigned)ntx);
+        tx = (int)(rem - (unsigned)ty * (unsigned)ntx);
+    }
+    int p_have = -1;
+    const uint8_t *cur = nullptr, *ref = nullptr;
+    for (unsigned item = first; item < nitems; item += nwarps, p += (int)step_p, ty += step_ty, tx += step_tx) {
+        if (tx >= ntx) { tx -= ntx; ++ty; }
+        if (ty >= nty) { ty -= nty; ++p; }
         const int x0 = tx * DCT_TILE_W, y0 = ty * 8;
         const int tw = min(DCT_TILE_W, W - x0);   // multiple of 8
         const bool g_on = g_c < tw, col_on = lane < tw, row_on = rp_blk * 8 < tw;
-        const uint8_t *cur = nullptr, *ref = nullptr;
-        if (a.has_fa) {
-            cur = cur_frame(a.fa, p);
-            ref = ref_frame(a.fa, p);
-        } else if (a.img) {
-            cur = a.img + (size_t)p * npix * 3;
+        if (p != p_have) {      // warp-uniform
+            p_have = p;
+            if (a.has_fa) {
+                const unsigned pg = (unsigned)(p + a.fa.p_off), gop = pg / (unsigned)a.fa.ppg, in_gop = pg - gop * (unsigned)a.fa.ppg;
+                cur = a.fa.cur_base + (long long)gop * a.fa.cur_gop_stride + (long long)in_gop * a.fa.cur_frame_stride;
+                ref = a.fa.ref_base + (long long)gop * a.fa.ref_gop_stride;
+            } else if (a.img) {
+                cur = a.img + (size_t)p * npix * 3;
+            }
         }
         const int16_t *mv = a.mv ? a.mv + (size_t)p * N * 2 : nullptr;
 
@@ -205,9 +249,13 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     const int B = byte_of(rw, 3 * u), G = byte_of(rw, 3 * u + 1), R = byte_of(rw, 3 * u + 2);
                     int Y, Cr, Cb;
                     bgr2ycrcb(B, G, R, Y, Cr, Cb);
-                    yv[u >> 2] |= (uint32_t)((Y - 128) & 0xff) << (8 * (u & 3));
-                    crv[u >> 2] |= (uint32_t)((Cr - 128) & 0xff) << (8 * (u & 3));
-                    cbv[u >> 2] |= (uint32_t)((Cb - 128) & 0xff) << (8 * (u & 3));
+                    yv[u >> 2] = put_byte(yv[u >> 2], (uint32_t)Y, u & 3);
+                    crv[u >> 2] = put_byte(crv[u >> 2], (uint32_t)Cr, u & 3);
+                    cbv[u >> 2] = put_byte(cbv[u >> 2], (uint32_t)Cb, u & 3);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {   // - 128 as int8 = flip bit 7 of every byte
+                    yv[h] ^= 0x80808080u; crv[h] ^= 0x80808080u; cbv[h] ^= 0x80808080u;
                 }
                 *reinterpret_cast<uint2 *>(s_in8 + (0 * 8 + g_r) * DCT_TILE_W + g_c) = make_uint2(yv[0], yv[1]);
                 *reinterpret_cast<uint2 *>(s_in8 + (1 * 8 + g_r) * DCT_TILE_W + g_c) = make_uint2(crv[0], crv[1]);
@@ -219,7 +267,14 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
         }
         __syncwarp();
 
-        const size_t gidx0 = (size_t)p * 3 * npix + (size_t)(y0 + rp_i) * W + x0 + rp_blk * 8;   // + ch * npix
+        // this lane's coefficient row of channel 0, advanced by one plane per channel (a running pointer: rebuilding the
+        // 64-bit index for every channel was 68 instructions per tile); the packed sink's outputs likewise
+        static_assert(DCT_NCH == 1, "the running pointers below advance one channel per pass group");
+        constexpr int ELEM = CM == 3 ? 1 : CM == 2 ? 2 : 8;
+        unsigned char *cptr = a.coef ? reinterpret_cast<unsigned char *>(a.coef) +
+            ((size_t)p * 3 * npix + (size_t)((unsigned)(y0 + rp_i) * (unsigned)W + (unsigned)(x0 + rp_blk * 8))) * ELEM : nullptr;
+        const unsigned brows = (unsigned)(H / 8), bcols = (unsigned)(W / 8);
+        size_t bidx = ((size_t)p * 3 * brows + (unsigned)ty) * bcols + (unsigned)(tx * 4 + rp_blk);   // block index, channel 0
         // Passes B-E run for NCH channels at a time (outer loop not unrolled): NCH = 3 fetches every DCT-matrix
         // constant once per 3 chains but needs ~120 registers and 3x the code; NCH = 1 halves both.
 #pragma unroll 1
@@ -257,11 +312,16 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
 #pragma unroll
                 for (int c = 0; c < DCT_NCH; ++c)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) tk[c][k] = s_x[c * 8 * DCT_RS + rbase0 + k];
+                    for (int k = 0; k < 8; k += 2) {
+                        const double2 t = *reinterpret_cast<const double2 *>(s_x + c * 8 * DCT_RS + rbase0 + k);
+                        tk[c][k] = t.x; tk[c][k + 1] = t.y;
+                    }
                 // All 8 chains first (one basic block: the DFMAs of different j interleave), then the quantiser.
                 // The rounded modes take q0 = D * RN(1/Q); a lane whose q0 comes within 2^-30 of a half-integer
-                // (|q0 - rint(q0)| > 0.5 - 2^-30) is re-done with the IEEE quotient in a rarely taken second pass.
-                constexpr double NEAR_HALF = 0.5 - 9.313225746154785e-10;
+                // is re-done with the IEEE quotient in a rarely taken second pass.  The test is on the high word of
+                // |q0 - rint(q0)| (two integer instructions per index): >= 0x3FDFFFFF means |.| >= 0.5 - 2^-22, which
+                // includes every value within 2^-30 of a half-integer; the extra second passes are exact too.
+                constexpr uint32_t NEAR_HALF_HI = 0x3FDFFFFFu;
                 double sj[DCT_NCH][8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -281,50 +341,56 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     uint32_t pk[4];
 #pragma unroll 1
                     for (int attempt = 0; attempt < 2; ++attempt) {
-                        bool near_half = false;
-                        double dprev = 0.0;
+                        uint32_t far = 0;               // max over the row of the high word of |q0 - rint(q0)|
+                        double dprev = 0.0, eprev = 0.0;
+                        double2 Q2 = make_double2(0.0, 0.0), rq2 = make_double2(0.0, 0.0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const double Q = s_q[ch * 64 + j * 8 + rp_i];
+                            if ((j & 1) == 0) {
+                                Q2 = *reinterpret_cast<const double2 *>(s_q + (ch * 8 + rp_i) * DCT_QS + j);
+                                if (coef_mode != 0) rq2 = *reinterpret_cast<const double2 *>(s_rq + (ch * 8 + rp_i) * DCT_QS + j);
+                            }
+                            const double Q = (j & 1) ? Q2.y : Q2.x;
                             double v;
                             if (coef_mode == 0) {
                                 v = sj[c][j] / Q;
                             } else if (!exact) {
-                                const double q0 = sj[c][j] * s_rq[ch * 64 + j * 8 + rp_i];
+                                const double q0 = sj[c][j] * ((j & 1) ? rq2.y : rq2.x);
                                 v = rint(q0);                              // np.round (dct.py:179) of RN(s/Q)
-                                near_half |= fabs(q0 - v) > NEAR_HALF;
+                                far = max(far, (uint32_t)__double2hiint(q0 - v) & 0x7fffffffu);
                             } else {
                                 v = rint(sj[c][j] / Q);                    // the exact quotient decides
                             }
                             if (has_coef) {
                                 if (coef_mode == 2) {
-                                    const uint32_t h = (uint32_t)(uint16_t)(int16_t)(int)v;
-                                    if (j & 1) pk[j >> 1] |= h << 16; else pk[j >> 1] = h;
+                                    pk[j >> 1] = put_half(pk[j >> 1], (uint32_t)(int)v, j & 1);
                                 } else if (coef_mode == 3) {   // int8: lossless when 1024 / min(Q) <= 127 (checked on the host)
-                                    const uint32_t h = (uint32_t)(uint8_t)(int8_t)(int)v;
-                                    if (j & 3) pk[j >> 2] |= h << (8 * (j & 3)); else pk[j >> 2] = h;
+                                    pk[j >> 2] = put_byte(pk[j >> 2], (uint32_t)(int)v, j & 3);
                                 } else if (j & 1) {
-                                    *reinterpret_cast<double2 *>(reinterpret_cast<double *>(a.coef) + gidx0 + ch * npix + j - 1) =
+                                    *reinterpret_cast<double2 *>(reinterpret_cast<double *>(cptr) + j - 1) =
                                         make_double2(dprev, v);
                                 } else {
                                     dprev = v;
                                 }
                             }
-                            if (do_inverse) s_x[c * 8 * DCT_RS + rbase0 + j] = v * Q;   // E = blk * Q (DCTcompressor.py:86)
+                            if (do_inverse) {                                           // E = blk * Q (DCTcompressor.py:86)
+                                if (j & 1) *reinterpret_cast<double2 *>(s_x + c * 8 * DCT_RS + rbase0 + j - 1) = make_double2(eprev, v * Q);
+                                else eprev = v * Q;
+                            }
                         }
                         if (has_coef && coef_mode == 2)
-                            *reinterpret_cast<uint4 *>(reinterpret_cast<int16_t *>(a.coef) + gidx0 + ch * npix) =
+                            *reinterpret_cast<uint4 *>(cptr) =
                                 make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         else if (has_coef && coef_mode == 3)
-                            *reinterpret_cast<uint2 *>(reinterpret_cast<int8_t *>(a.coef) + gidx0 + ch * npix) =
+                            *reinterpret_cast<uint2 *>(cptr) =
                                 make_uint2(pk[0], pk[1]);
-                        if (exact || !near_half) break;   // per lane; the second attempt redoes this lane's row exactly
+                        if (exact || far < NEAR_HALF_HI) break;   // per lane; the second attempt redoes this lane's row exactly
                         exact = true;
                     }
                     if (PATH == DCT_FWD && coef_mode == 3 && a.bitmap) {
                         // occupancy of this lane's 8 indices = byte rp_i of the block's bitmap; 32 lanes = 32 consecutive bytes
                         const uint32_t m8 = nz_nibble(pk[0]) | (nz_nibble(pk[1]) << 4);
-                        a.bitmap[(((size_t)p * 3 + ch) * (H / 8) + ty) * (size_t)(W / 8) * 8 + (size_t)(tx * 4 + rp_blk) * 8 + rp_i] = (uint8_t)m8;
+                        a.bitmap[bidx * 8 + rp_i] = (uint8_t)m8;
                         // low half: non-zero indices, high half: those outside [-8, 7] (escapes of the nibble code)
                         nnz_lane[c] = __popc(m8) | ((__popc(esc_nibble(pk[0])) + __popc(esc_nibble(pk[1]))) << 16);
                     }
@@ -338,7 +404,7 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     for (int o = 1; o < 8; o <<= 1) n += __shfl_xor_sync(0xffffffffu, n, o);     // the block's 8 rows
                     const uint32_t esc = n >> 16;
                     if (row_on && rp_i == 0)
-                        a.blk_esc[(((size_t)p * 3 + ch0 + c) * (H / 8) + ty) * (size_t)(W / 8) + tx * 4 + rp_blk] = (uint8_t)esc;
+                        a.blk_esc[bidx] = (uint8_t)esc;
                     unsigned long long t = (((n & 0xffffu) + 1) >> 1) | ((unsigned long long)esc << 32);   // nibble bytes | escapes
 #pragma unroll
                     for (int o = 8; o < 32; o <<= 1) t += shfl_xor_u64(t, o);                    // the tile's 4 blocks
@@ -352,16 +418,16 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                 const int ch = ch0 + c;
                 double qv[8];
                 if (coef_mode == 2) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(reinterpret_cast<const int16_t *>(a.coef) + gidx0 + ch * npix);
+                    const uint4 v = *reinterpret_cast<const uint4 *>(cptr);
                     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int j = 0; j < 8; ++j) qv[j] = (double)(int)(int16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
                 } else if (coef_mode == 3) {
-                    const uint2 v = *reinterpret_cast<const uint2 *>(reinterpret_cast<const int8_t *>(a.coef) + gidx0 + ch * npix);
+                    const uint2 v = *reinterpret_cast<const uint2 *>(cptr);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) qv[j] = (double)(int)(int8_t)(((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xff);
                 } else {
-                    const double *o = reinterpret_cast<const double *>(a.coef) + gidx0 + ch * npix;
+                    const double *o = reinterpret_cast<const double *>(cptr);
 #pragma unroll
                     for (int j = 0; j < 8; j += 2) {
                         const double2 v = *reinterpret_cast<const double2 *>(o + j);
@@ -369,7 +435,7 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) s_x[c * 8 * DCT_RS + rbase0 + j] = qv[j] * s_q[ch * 64 + j * 8 + rp_i];
+                for (int j = 0; j < 8; ++j) s_x[c * 8 * DCT_RS + rbase0 + j] = qv[j] * s_q[(ch * 8 + rp_i) * DCT_QS + j];
             }
         }
         if (do_inverse) {
@@ -403,7 +469,10 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
 #pragma unroll
                 for (int c = 0; c < DCT_NCH; ++c)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) tk[c][k] = s_x[c * 8 * DCT_RS + rbase0 + k];
+                    for (int k = 0; k < 8; k += 2) {
+                        const double2 t = *reinterpret_cast<const double2 *>(s_x + c * 8 * DCT_RS + rbase0 + k);
+                        tk[c][k] = t.x; tk[c][k + 1] = t.y;
+                    }
                 uint32_t w[DCT_NCH][2];
 #pragma unroll
                 for (int c = 0; c < DCT_NCH; ++c) w[c][0] = w[c][1] = 0;
@@ -420,14 +489,17 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     }
                     // float64 -> uint8 store (DCTcompressor.py:81,88): truncate toward zero, low 8 bits; then +128
 #pragma unroll
-                    for (int c = 0; c < DCT_NCH; ++c)
-                        w[c][j >> 2] |= (((uint32_t)(long long)s[c] + 128u) & 0xffu) << (8 * (j & 3));
+                    for (int c = 0; c < DCT_NCH; ++c) w[c][j >> 2] = put_byte(w[c][j >> 2], (uint32_t)(long long)s[c], j & 3);
                 }
+#pragma unroll
+                for (int c = 0; c < DCT_NCH; ++c) { w[c][0] ^= 0x80808080u; w[c][1] ^= 0x80808080u; }   // + 128 (mod 256)
 #pragma unroll
                 for (int c = 0; c < DCT_NCH; ++c)
                     *reinterpret_cast<uint2 *>(s_out + ((ch0 + c) * 8 + rp_i) * DCT_TILE_W + rp_blk * 8) = make_uint2(w[c][0], w[c][1]);
             }
         }
+        if (cptr) cptr += npix * ELEM;
+        bidx += (size_t)brows * bcols;
         }   // channel groups
         if (do_inverse) {
             __syncwarp();
@@ -438,16 +510,15 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                 const uint2 cbv = *reinterpret_cast<const uint2 *>(s_out + (2 * 8 + g_r) * DCT_TILE_W + g_c);
                 const uint32_t *sp = reinterpret_cast<const uint32_t *>(s_pred + (g_r * DCT_TILE_W + g_c) * 3);
                 uint32_t ow[6] = {0, 0, 0, 0, 0, 0};
+                const uint32_t yw[2] = {yv.x, yv.y}, crw[2] = {crv.x, crv.y}, cbw[2] = {cbv.x, cbv.y};
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int sh = 8 * (u & 3);
-                    const int Y = ((u < 4 ? yv.x : yv.y) >> sh) & 0xff, Cr = ((u < 4 ? crv.x : crv.y) >> sh) & 0xff,
-                              Cb = ((u < 4 ? cbv.x : cbv.y) >> sh) & 0xff;
+                    const int Y = byte_of(yw, u), Cr = byte_of(crw, u), Cb = byte_of(cbw, u);
                     int B, G, R;
                     ycrcb2bgr(Y, Cr, Cb, B, G, R);
-                    ow[(3 * u) >> 2] |= (uint32_t)B << (8 * ((3 * u) & 3));
-                    ow[(3 * u + 1) >> 2] |= (uint32_t)G << (8 * ((3 * u + 1) & 3));
-                    ow[(3 * u + 2) >> 2] |= (uint32_t)R << (8 * ((3 * u + 2) & 3));
+                    ow[(3 * u) >> 2] = put_byte(ow[(3 * u) >> 2], (uint32_t)B, (3 * u) & 3);
+                    ow[(3 * u + 1) >> 2] = put_byte(ow[(3 * u + 1) >> 2], (uint32_t)G, (3 * u + 1) & 3);
+                    ow[(3 * u + 2) >> 2] = put_byte(ow[(3 * u + 2) >> 2], (uint32_t)R, (3 * u + 2) & 3);
                 }
                 uint32_t ov[6];   // pred + decoded, uint8 wrap (decoder.py:57)
 #pragma unroll

@@ -145,7 +145,8 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     uint8_t *s_out = reinterpret_cast<uint8_t *>(s_in8 + DCT_PLANE);              // [3][8][32] decoded YCrCb
 
     const int W = a.W, H = a.H, bs = a.bs, nbx = a.nbx, nby = a.nby;
-    const size_t npix = (size_t)H * W;
+    size_t npix = (size_t)H * W;
+    asm volatile("" : "+l"(npix));   // pinned like lane below: the 64-bit product was rebuilt at every use
     const int N = nbx * nby;
 
     // [ch][i][QS]: in the row passes a lane (block, row i) reads its 8 divisors as 4 aligned 16-byte words
@@ -166,7 +167,8 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     // lane roles
     const int g_r = lane >> 2, g_c = (lane & 3) * 8;        // stages A/F: 8-pixel group (row, first column)
     const int rp_i = lane & 7, rp_blk = lane >> 3;          // row passes: row i of block blk
-    const int rbase0 = rp_i * DCT_RS + rp_blk * 8;          // + ch * 8 * RS
+    int rbase0 = rp_i * DCT_RS + rp_blk * 8;                // + ch * 8 * RS
+    asm volatile("" : "+r"(rbase0));
 
     // The warp walks items first, first + nwarps, ...: (p, ty, tx) advance by constant steps with two carries, and the
     // frame pointers are refreshed only when p changes -- the divisions this replaces were 100 instructions per tile.
@@ -179,6 +181,10 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
         ty = (int)(rem / (unsigned)ntx);
         tx = (int)(rem - (unsigned)ty * (unsigned)ntx);
     }
+    // Row 0 of the DCT matrix is the single value 1/sqrt(8) (vcs_dct_matrix, like _dctMatrix()): it lives in a register, which
+    // saves the constant fetches of one chain in 8 in every pass.
+    double a0 = c_dct[0];
+    asm volatile("" : "+d"(a0));
     int p_have = -1;
     const uint8_t *cur = nullptr, *ref = nullptr;
     for (unsigned item = first; item < nitems; item += nwarps, p += (int)step_p, ty += step_ty, tx += step_tx) {
@@ -271,8 +277,8 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
         // 64-bit index for every channel was 68 instructions per tile); the packed sink's outputs likewise
         static_assert(DCT_NCH == 1, "the running pointers below advance one channel per pass group");
         constexpr int ELEM = CM == 3 ? 1 : CM == 2 ? 2 : 8;
-        unsigned char *cptr = a.coef ? reinterpret_cast<unsigned char *>(a.coef) +
-            ((size_t)p * 3 * npix + (size_t)((unsigned)(y0 + rp_i) * (unsigned)W + (unsigned)(x0 + rp_blk * 8))) * ELEM : nullptr;
+        unsigned char *cptr = reinterpret_cast<unsigned char *>(a.coef) +     // never dereferenced when there is no coefficient buffer
+            ((size_t)p * 3 * npix + (size_t)((unsigned)(y0 + rp_i) * (unsigned)W + (unsigned)(x0 + rp_blk * 8))) * ELEM;
         const unsigned brows = (unsigned)(H / 8), bcols = (unsigned)(W / 8);
         size_t bidx = ((size_t)p * 3 * brows + (unsigned)ty) * bcols + (unsigned)(tx * 4 + rp_blk);   // block index, channel 0
         // Passes B-E run for NCH channels at a time (outer loop not unrolled): NCH = 3 fetches every DCT-matrix
@@ -294,7 +300,7 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     for (int c = 0; c < DCT_NCH; ++c) s[c] = 0.0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double cc = c_dct[i * 8 + k];
+                        const double cc = i == 0 ? a0 : c_dct[i * 8 + k];
 #pragma unroll
                         for (int c = 0; c < DCT_NCH; ++c) s[c] = __fma_rn(cc, xk[c][k], s[c]);
                     }
@@ -329,7 +335,7 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     for (int c = 0; c < DCT_NCH; ++c) sj[c][j] = 0.0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double cc = c_dct[j * 8 + k];
+                        const double cc = j == 0 ? a0 : c_dct[j * 8 + k];
 #pragma unroll
                         for (int c = 0; c < DCT_NCH; ++c) sj[c][j] = __fma_rn(tk[c][k], cc, sj[c][j]);
                     }
@@ -454,7 +460,7 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     for (int c = 0; c < DCT_NCH; ++c) s[c] = 0.0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double cc = c_dct[k * 8 + i];
+                        const double cc = k == 0 ? a0 : c_dct[k * 8 + i];
 #pragma unroll
                         for (int c = 0; c < DCT_NCH; ++c) s[c] = __fma_rn(cc, ek[c][k], s[c]);
                     }
@@ -483,7 +489,7 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     for (int c = 0; c < DCT_NCH; ++c) s[c] = 0.0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double cc = c_dct[k * 8 + j];
+                        const double cc = k == 0 ? a0 : c_dct[k * 8 + j];
 #pragma unroll
                         for (int c = 0; c < DCT_NCH; ++c) s[c] = __fma_rn(tk[c][k], cc, s[c]);
                     }
@@ -498,7 +504,7 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                     *reinterpret_cast<uint2 *>(s_out + ((ch0 + c) * 8 + rp_i) * DCT_TILE_W + rp_blk * 8) = make_uint2(w[c][0], w[c][1]);
             }
         }
-        if (cptr) cptr += npix * ELEM;
+        cptr += npix * ELEM;
         bidx += (size_t)brows * bcols;
         }   // channel groups
         if (do_inverse) {

@@ -109,3 +109,28 @@ def test_small_escape_buffer_is_refused():
     out = ce.alloc_host_packed(T, pinned=False, escape_fraction=0.0)       # 64 bytes only
     with pytest.raises(v.VcsError, match="too small"):
         ce.encode_host_packed(clip, out)
+
+
+def test_damaged_packed_clip_is_refused():
+    """Decoding a packed clip whose row counts do not add up to the stream lengths is refused on the host; one whose
+    bitmaps claim more indices than its streams hold never reads past their end and fails on the device check."""
+    import vcs_h264_b200 as v
+    from vcs_h264_b200 import synth
+    T, H, W = 5, 64, 96
+    clip = synth.clip(T, H, W, seed=11, margin=48)
+    ce = v.ClipEncoder([H, W], block_size=16, search="full", search_range=8, gop_len=4, qf=50.0, coef_mode=v.COEF_I8_RINT)
+    pk = ce.encode_host_packed(clip, want_recon=True)
+    cd = v.ClipDecoder([H, W], block_size=16, gop_len=4, qf=50.0, coef_mode=v.COEF_I8_RINT)
+    args = lambda **kw: [kw.get(k, pk[k]) for k in ("mv", "bitmap", "row_count", "nibbles", "escapes", "lengths")]
+    good = cd.decode_host_packed(clip[::4], *args(), T)
+    assert np.array_equal(good, np.asarray(pk["recon"]))
+    rc = np.array(np.asarray(pk["row_count"]), copy=True)
+    rc.reshape(-1)[0] += 1
+    with pytest.raises(v.VcsError, match="do not add up"):
+        cd.decode_host_packed(clip[::4], *args(row_count=rc), T)
+    bm = np.array(np.asarray(pk["bitmap"]), copy=True)
+    bm.reshape(-1).view(np.uint8)[-8:] = 0xFF                  # the last block now claims 64 indices
+    with pytest.raises(v.VcsError):
+        cd.decode_host_packed(clip[::4], *args(bitmap=bm), T)
+    again = cd.decode_host_packed(clip[::4], *args(), T)          # the context is usable afterwards
+    assert np.array_equal(again, good)

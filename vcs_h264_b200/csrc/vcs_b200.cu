@@ -11,6 +11,7 @@
 #include <string.h>
 #include <time.h>
 
+#include <chrono>
 #include <vector>
 
 #include "../../include/vcs_b200.h"
@@ -935,7 +936,10 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
             left -= tail_sum;
             for (int k = 0; left > 0; ++k) {
                 int n = k < 5 ? head[k] : 8;
-                if (n > left) n = left; else if (k > 0) { n = nudge(n, left); }
+                // the ramp is paced by the upload (a segment's frames must have arrived when the previous segment's
+                // kernels end: 1,2,4 stalls the third segment for 0.16 ms at 1080p where 1,2,3 does not), so only the
+                // full-size segments are nudged
+                if (n > left) n = left; else if (k >= 5) { n = nudge(n, left); }
                 sizes.push_back(n);
                 left -= n;
             }
@@ -968,8 +972,12 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
     const bool trace = getenv("VCS_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev;
     auto tmark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
-    const double host_t0 = trace ? (double)clock() / CLOCKS_PER_SEC : 0.0;
-    if (trace) { cudaStreamSynchronize(ctx->stream); tmark(ctx->stream); cudaStreamWaitEvent(ctx->s_h2d, tev[0], 0); cudaStreamWaitEvent(ctx->s_d2h, tev[0], 0); }
+    std::vector<double> host_ms;          // when the host had queued each segment's kernels, on the same time base
+    std::chrono::steady_clock::time_point host_t0;
+    if (trace) {
+        cudaStreamSynchronize(ctx->stream); tmark(ctx->stream); cudaStreamWaitEvent(ctx->s_h2d, tev[0], 0); cudaStreamWaitEvent(ctx->s_d2h, tev[0], 0);
+        host_t0 = std::chrono::steady_clock::now();
+    }
     // (Running consecutive searches on two streams so that one fills the other's tail was tried and is slower:
     // the persistent search CTAs of the next chunk then keep the DCT stage of this chunk off the SMs.)
     // Optional two-stream schedule (VCS_TILES_PER_CTA=k > 0): searches back to back on a low-priority stream with k
@@ -1049,6 +1057,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
                 return rc;
         }
         CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sd));
+        if (trace) host_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
         tmark(sd);           // 3 + 4c: compute of segment c done
         if (pk) {
             CK(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->chunk_events[2 * c + 1], 0));
@@ -1095,13 +1104,14 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
                 e4 = cudaStreamSynchronize(ctx->s_aux), e5 = cudaStreamSynchronize(sd);
     if (trace && !tev.empty()) {
         auto ms = [&](size_t k) { float t = 0; cudaEventElapsedTime(&t, tev[0], tev[k]); return t; };
-        fprintf(stderr, "[vcs trace] %d segments, %s sink; per segment: P-frames | upload done, compute start, compute done, download done (ms)\n",
+        fprintf(stderr, "[vcs trace] %d segments, %s sink; per segment: P-frames | upload done, compute start, compute done, download done | host had queued the kernels (ms)\n",
                 nsegs, pk ? "packed" : "dense");
         for (int c = 0; c < nsegs; ++c) {
             const size_t b = 1 + (size_t)(pk ? 3 : 4) * c;
             const size_t dl = pk ? 1 + 3 * (size_t)nsegs + c : b + 3;
             if (dl < tev.size())
-                fprintf(stderr, "[vcs trace] seg %2d np %2d | %7.3f %7.3f %7.3f %7.3f\n", c, sizes[c], ms(b), ms(b + 1), ms(b + 2), ms(dl));
+                fprintf(stderr, "[vcs trace] seg %2d np %2d | %7.3f %7.3f %7.3f %7.3f | %7.3f\n", c, sizes[c], ms(b), ms(b + 1), ms(b + 2), ms(dl),
+                        c < (int)host_ms.size() ? host_ms[c] : -1.0);
         }
         for (auto e : tev) cudaEventDestroy(e);
     }

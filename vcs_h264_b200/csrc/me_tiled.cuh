@@ -33,6 +33,9 @@
 // the ALU pipe (IADD3), the rest go to the FMA pipe (IMAD.IADD).  Round-2 A/B of 18 splits on one B200 (tools/ab_me.sh +
 // tools/ab_run.sh, two runs each, 45 P-frames): 0xa/5 9.02 ms, 0x9/5 9.05, 0x29/8 9.06, 0x6/5 9.10, ... 0x1/2 9.24 -- the
 // instruction mix is the same for equal ratios, only the ptxas schedule differs.
+#ifndef VCS_CUR_PAD
+#define VCS_CUR_PAD 4
+#endif
 #ifndef VCS_WRAP_ALU_MASK
 #define VCS_WRAP_ALU_MASK 0xa
 #define VCS_WRAP_ALU_DEN 5
@@ -78,7 +81,11 @@ struct TiledCfg {
     static constexpr size_t SZ_CRAW = (size_t)CURW * CURR * 4;
     static constexpr size_t SZ_CRAW_AL = (SZ_CRAW + 127) / 128 * 128;
     static constexpr size_t OFF_CURT = OFF_CRAW + SZ_CRAW_AL;
-    static constexpr size_t SZ_CURT = (size_t)NMB * WPR * BS * 4;      // [mb][w][v]
+    // macroblock words [mb][w][v], macroblocks CURS words apart: +4 (one 16-byte bank group) so that the lanes of the warp
+    // that holds dx = ND-1 of ALL macroblocks read different banks (a stride of WPR*BS = 0 mod 32 words made its 8
+    // LDS.128 per word column 15-way conflicts; the macroblock warps' loads are broadcasts either way)
+    static constexpr int CURS = WPR * BS + VCS_CUR_PAD;
+    static constexpr size_t SZ_CURT = (size_t)NMB * CURS * 4;
     static constexpr size_t OFF_MISC = (OFF_CURT + 2 * SZ_CURT + 127) / 128 * 128;  // 2: wrap8 L/H
     static constexpr size_t SZ_MISC = 8 * NMB + 8 * NMB + 4 * NMB + 4 * NMB + 64;
     static constexpr size_t SMEM = OFF_MISC + SZ_MISC + 128;
@@ -149,7 +156,7 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     extern __shared__ __align__(128) unsigned char smem[];
     uint32_t *sT = reinterpret_cast<uint32_t *>(smem + C::OFF_T);
     uint32_t *sCurT = reinterpret_cast<uint32_t *>(smem + C::OFF_CURT);           // SAD: c ; wrap8: c & ~H
-    uint32_t *sCurH = sCurT + NMB * WPR * BS;                                      // wrap8: c & H
+    uint32_t *sCurH = sCurT + NMB * C::CURS;                                       // wrap8: c & H
     unsigned long long *sBest = reinterpret_cast<unsigned long long *>(smem + C::OFF_MISC);
     unsigned long long *sDyMask = sBest + NMB;                                     // valid dy bits per mb
     uint32_t *sStatic = reinterpret_cast<uint32_t *>(sDyMask + NMB);               // 0 / 1 per mb
@@ -256,8 +263,9 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
             for (int k = tid; k < NMB * WPR * BS; k += C::THREADS) {
                 const int v = k % BS, w = (k / BS) % WPR, m = k / (BS * WPR);
                 const uint32_t c = craw[((m / MX) * BS + v) * C::CURW + cao + (m % MX) * WPR + w];
-                if (METRIC == 0) { sCurT[k] = c & ~Hm; sCurH[k] = c & Hm; }
-                else sCurT[k] = c;
+                const int kd = m * C::CURS + w * BS + v;
+                if (METRIC == 0) { sCurT[kd] = c & ~Hm; sCurH[kd] = c & Hm; }
+                else sCurT[kd] = c;
             }
             if (tid < NMB) {
                 if (first) { sBest[tid] = ~0ull; sStatic[tid] = 0; }
@@ -285,8 +293,8 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
                 for (int k = lane; k < WPR * BS; k += 32) {
                     const int w = k / BS, v = k - w * BS;
                     const uint32_t r = col[w * RP + v];
-                    uint32_t c = sCurT[(m * WPR + w) * BS + v];
-                    if (METRIC == 0) c |= sCurH[(m * WPR + w) * BS + v];
+                    uint32_t c = sCurT[m * C::CURS + w * BS + v];
+                    if (METRIC == 0) c |= sCurH[m * C::CURS + w * BS + v];
                     sad = sad4_acc(r, c, sad);
                     sr = bytesum_acc(r, sr);
                     sc = bytesum_acc(c, sc);
@@ -314,8 +322,8 @@ me_tiled_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
         if (active && dymask) {
             const int sb = ao + 3 * (BS * mbx + dxw);
             const uint32_t *col = sT + (sb & 3) * PS + (sb >> 2) * RP + BS * mby;
-            const uint32_t *cl = sCurT + mb * WPR * BS;
-            const uint32_t *ch = sCurH + mb * WPR * BS;
+            const uint32_t *cl = sCurT + mb * C::CURS;
+            const uint32_t *ch = sCurH + mb * C::CURS;
             // wrap8 accumulates 64 * byte-sum (IDP.4A with every multiplier byte = 64), so that the argmin key
             // cost * 64 + d below needs no shift; SAD (VABSDIFF4.ACC adds plain bytes) scales at the end.
             constexpr uint32_t WRAP_MUL = 0x40404040u, KEY_MUL = METRIC == 0 ? 1u : 64u;

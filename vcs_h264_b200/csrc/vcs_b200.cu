@@ -991,7 +991,11 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
     const bool two_streams = tiles_per_cta > 0;
     cudaStream_t sc = two_streams ? ctx->s_search : ctx->stream;
     cudaStream_t sd = two_streams ? ctx->s_dct : ctx->stream;
-    while (two_streams && (int)ctx->me_events.size() < nsegs) {
+    // VCS_PACK_ASIDE=0 keeps the packing kernels on the compute stream (11.14 ms per bench clip against 10.83 ms on the side stream)
+    const bool pack_aside = pk && !two_streams && !(getenv("VCS_PACK_ASIDE") && atoi(getenv("VCS_PACK_ASIDE")) == 0);
+    // (The DCT stage itself on a side stream, overlapping the next search's last wave with the search after that waiting for
+    // it, measured slower: 10.95 ms against 10.55 ms dense, 10.94 against 10.81 packed.)
+    while ((two_streams || pack_aside) && (int)ctx->me_events.size() < nsegs) {
         cudaEvent_t e;
         CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ctx->me_events.push_back(e);
@@ -1039,6 +1043,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
         }
         tmark(ctx->s_h2d);   // 1 + 4c: upload of segment c done
         tmark(sc);           // 2 + 4c: compute of segment c may start (previous compute done)
+        cudaStream_t sdone = sd;   // the stream whose progress makes segment c ready for download
         {
             const int g0 = p0 / ppg;
             FrameAddr fa = clip_addr(d_fr + fs * (size_t)g0 * gop_len, p->H, p->W, gop_len);
@@ -1052,11 +1057,18 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
                             pk ? pd.row_count + (size_t)p0 * rows_per_p : nullptr,
                             two_streams ? sd : nullptr, two_streams ? ctx->me_events[c] : nullptr);
             if (rc) return rc;
-            if (pk && (rc = launch_pack(ctx, sd, p->H, p->W, np, (const int8_t *)d_coef + (size_t)p0 * npix * 3, pd,
+            // Packing is not on the compute chain (only this segment's download needs it): on its own stream it runs in
+            // the SMs the NEXT segment's search leaves idle in its last partial wave instead of delaying that search.
+            if (pk && pack_aside) {
+                CK(ctx, cudaEventRecord(ctx->me_events[c], sd));
+                CK(ctx, cudaStreamWaitEvent(ctx->s_dct, ctx->me_events[c], 0));
+                sdone = ctx->s_dct;
+            }
+            if (pk && (rc = launch_pack(ctx, sdone, p->H, p->W, np, (const int8_t *)d_coef + (size_t)p0 * npix * 3, pd,
                                         (size_t)p0 * rows_per_p, pd.totals + 2 + 2 * c, d_rec == nullptr)))
                 return rc;
         }
-        CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sd));
+        CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sdone));
         if (trace) host_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
         tmark(sd);           // 3 + 4c: compute of segment c done
         if (pk) {
@@ -1102,6 +1114,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
     // success or not, nothing may still be reading or writing the caller's buffers when this returns
     cudaError_t e1 = cudaStreamSynchronize(ctx->s_h2d), e2 = cudaStreamSynchronize(sc), e3 = cudaStreamSynchronize(ctx->s_d2h),
                 e4 = cudaStreamSynchronize(ctx->s_aux), e5 = cudaStreamSynchronize(sd);
+    if (pack_aside) { const cudaError_t e6 = cudaStreamSynchronize(ctx->s_dct); if (e5 == cudaSuccess) e5 = e6; }
     if (trace && !tev.empty()) {
         auto ms = [&](size_t k) { float t = 0; cudaEventElapsedTime(&t, tev[0], tev[k]); return t; };
         fprintf(stderr, "[vcs trace] %d segments, %s sink; per segment: P-frames | upload done, compute start, compute done, download done | host had queued the kernels (ms)\n",

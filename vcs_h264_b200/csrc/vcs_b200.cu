@@ -970,8 +970,15 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
     }
     // VCS_TRACE=1: a timeline of the pipeline on stderr (timing-enabled events; diagnostics only)
     const bool trace = getenv("VCS_TRACE") != nullptr;
-    std::vector<cudaEvent_t> tev;
-    auto tmark = [&](cudaStream_t st) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+    std::vector<cudaEvent_t> tev;          // [0]: start of the call; then 4 per segment: upload done, compute may start, compute done, download done
+    auto tmark = [&](cudaStream_t st, int seg = -1, int what = 0) {
+        if (!trace) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st);
+        if (seg < 0) { tev.push_back(e); return; }
+        const size_t k = 1 + 4 * (size_t)seg + (size_t)what;
+        if (tev.size() <= k) tev.resize(k + 1, nullptr);
+        tev[k] = e;
+    };
     std::vector<double> host_ms;          // when the host had queued each segment's kernels, on the same time base
     std::chrono::steady_clock::time_point host_t0;
     if (trace) {
@@ -1030,19 +1037,31 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
     };
     auto pipeline = [&]() -> int {
     int uploaded = 0, p0 = 0;
-    for (int c = 0; c < nsegs; ++c) {                    // frames after the last P-frame are never needed on the device
-        const int np = sizes[c];
-        const int plast = p0 + np - 1;
-        const int t_need = (plast / ppg) * gop_len + 1 + plast % ppg + 1;   // frames [0, t_need) must be resident
-        if (t_need > uploaded) {
-            CK(ctx, cudaMemcpyAsync(d_fr + fs * uploaded, frames + fs * uploaded, fs * (t_need - uploaded),
+    // frames [0, need(c)) must be resident for segment c; frames after the last P-frame are never needed on the device
+    std::vector<int> need(nsegs);
+    for (int c = 0, q = 0; c < nsegs; q += sizes[c], ++c) {
+        const int plast = q + sizes[c] - 1;
+        need[c] = (plast / ppg) * gop_len + 1 + plast % ppg + 1;
+    }
+    std::vector<char> has_upload(nsegs, 0);
+    auto upload = [&](int c) -> int {           // queue segment c's frames; chunk_events[2c] = they have arrived
+        if (need[c] > uploaded) {
+            CK(ctx, cudaMemcpyAsync(d_fr + fs * uploaded, frames + fs * uploaded, fs * (need[c] - uploaded),
                                     cudaMemcpyHostToDevice, ctx->s_h2d));
             CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c], ctx->s_h2d));
-            CK(ctx, cudaStreamWaitEvent(sc, ctx->chunk_events[2 * c], 0));
-            uploaded = t_need;
+            uploaded = need[c];
+            has_upload[c] = 1;
         }
-        tmark(ctx->s_h2d);   // 1 + 4c: upload of segment c done
-        tmark(sc);           // 2 + 4c: compute of segment c may start (previous compute done)
+        tmark(ctx->s_h2d, c, 0);
+        return VCS_OK;
+    };
+    // (Waiting for segment c+1's frames between the search and the DCT stage of segment c, so that the cross-stream wait
+    // hides behind a running search, was tried against the ~40 us bubble between the first segments: no change.)
+    for (int c = 0; c < nsegs; ++c) {
+        const int np = sizes[c];
+        if ((rc = upload(c))) return rc;
+        if (has_upload[c]) CK(ctx, cudaStreamWaitEvent(sc, ctx->chunk_events[2 * c], 0));
+        tmark(sc, c, 1);
         cudaStream_t sdone = sd;   // the stream whose progress makes segment c ready for download
         {
             const int g0 = p0 / ppg;
@@ -1070,7 +1089,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
         }
         CK(ctx, cudaEventRecord(ctx->chunk_events[2 * c + 1], sdone));
         if (trace) host_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
-        tmark(sd);           // 3 + 4c: compute of segment c done
+        tmark(sd, c, 2);
         if (pk) {
             CK(ctx, cudaStreamWaitEvent(ctx->s_aux, ctx->chunk_events[2 * c + 1], 0));
             CK(ctx, cudaMemcpyAsync(&ctx->h_segend[2 * c], pd.totals + 2 + 2 * c, 16, cudaMemcpyDeviceToHost, ctx->s_aux));
@@ -1078,7 +1097,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
         } else {
             CK(ctx, cudaStreamWaitEvent(ctx->s_d2h, ctx->chunk_events[2 * c + 1], 0));
             if (np > 0 && (rc = download(p0, np))) return rc;
-            tmark(ctx->s_d2h);   // 4 + 4c: download of segment c done (dense sink)
+            tmark(ctx->s_d2h, c, 3);
         }
         p0 += np;
     }
@@ -1103,7 +1122,7 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
                                     (size_t)np * rows_per_p * 8, cudaMemcpyDeviceToHost, ctx->s_d2h));
             if ((rc = download(p0, np))) return rc;
         }
-        tmark(ctx->s_d2h);       // 4 + 4c (packed sink: appended after the pass-1 marks): download of segment c done
+        tmark(ctx->s_d2h, c, 3);
         have_n = end_n; have_e = end_e;
         pk->lengths[0] = have_n; pk->lengths[1] = have_e;
         p0 += np;
@@ -1120,13 +1139,12 @@ static int encode_clip_host_impl(vcs_ctx *ctx, const vcs_me_params *p, const uin
         fprintf(stderr, "[vcs trace] %d segments, %s sink; per segment: P-frames | upload done, compute start, compute done, download done | host had queued the kernels (ms)\n",
                 nsegs, pk ? "packed" : "dense");
         for (int c = 0; c < nsegs; ++c) {
-            const size_t b = 1 + (size_t)(pk ? 3 : 4) * c;
-            const size_t dl = pk ? 1 + 3 * (size_t)nsegs + c : b + 3;
-            if (dl < tev.size())
-                fprintf(stderr, "[vcs trace] seg %2d np %2d | %7.3f %7.3f %7.3f %7.3f | %7.3f\n", c, sizes[c], ms(b), ms(b + 1), ms(b + 2), ms(dl),
+            const size_t b = 1 + 4 * (size_t)c;
+            if (b + 3 < tev.size() && tev[b] && tev[b + 1] && tev[b + 2] && tev[b + 3])
+                fprintf(stderr, "[vcs trace] seg %2d np %2d | %7.3f %7.3f %7.3f %7.3f | %7.3f\n", c, sizes[c], ms(b), ms(b + 1), ms(b + 2), ms(b + 3),
                         c < (int)host_ms.size() ? host_ms[c] : -1.0);
         }
-        for (auto e : tev) cudaEventDestroy(e);
+        for (auto e : tev) if (e) cudaEventDestroy(e);
     }
     if (rc) return rc;
     CK(ctx, e1); CK(ctx, e2); CK(ctx, e3); CK(ctx, e4); CK(ctx, e5);

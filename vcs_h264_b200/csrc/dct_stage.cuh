@@ -20,9 +20,9 @@
 // are always in different stages and hide each other's latencies:
 //   A  lane = one 8-pixel group: cur (3 x LDG.64) and the motion-compensated prediction (aligned
 //      words + funnel shift), residual, BGR->YCrCb-128 packed as int8 into shared memory;
-//   then, one channel at a time (DCT_NCH = 1; the loop is not unrolled, which keeps the kernel at 58-64
-//   registers = 8 CTAs of 4 warps per SM and a third of the code):
-//   B  lane = one pixel column: 8 inputs in registers, 8 DFMA chains, results in place (doubles, row stride 33);
+//   then, one channel at a time (DCT_NCH = 1; the loop is not unrolled, which keeps the kernel at <= 72
+//   registers = 7 CTAs of 4 warps per SM and a third of the code):
+//   B  lane = one pixel column: 8 inputs in registers, 8 DFMA chains, results in place (doubles, row stride 34);
 //   C  lane = (block, row): row pass (all 8 chains first), quantise, coefficients straight to global
 //      memory (8 int8 / int16 = one STG.64 / STG.128), E = q*Q back in place;
 //   D/E the inverse column and row passes the same way, truncating store into packed bytes;
@@ -32,7 +32,7 @@
 //
 // Quantiser: the reference computes rint(RN(D/Q)).  For the rounded modes the kernel takes
 // q0 = D * RN(1/Q) (within 2^-40 of the true quotient for |q| < 2^11) and only when q0 lies within
-// 2^-30 of a half-integer re-does that lane's row with the IEEE divide, so the result is bit-identical
+// 2^-22 of a half-integer re-does that lane's row with the IEEE divide, so the result is bit-identical
 // while the common path costs a DMUL.  The un-rounded mode (the reference's inter path,
 // DCTcompressor.py:71) always uses the IEEE divide.
 #pragma once

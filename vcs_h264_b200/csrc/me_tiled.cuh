@@ -8,13 +8,15 @@
 // Design (INT32-ALU bound; DESIGN.md "me_tiled"):
 //   * persistent CTAs, one per SM; a work unit is (tile of MX x MY macroblocks, ND x ND chunk of
 //     the offset range).  The reference window of a unit is fetched by ONE TMA tile load
-//     (cp.async.bulk.tensor, zero fill outside the frame) into a double-buffered raw stage while
-//     the previous unit is being searched; the tile's macroblocks come by a second TMA load.
+//     (cp.async.bulk.tensor, zero fill outside the frame) into ONE raw stage: it is free again as soon as the
+//     window has been re-laid, so the next unit's loads are issued right then and land while this
+//     unit is being searched; the tile's macroblocks come by a second TMA load.
 //   * frames are BGR-interleaved, so a dx shift is 3 bytes and 3 of 4 candidates are not word
 //     aligned.  The raw window is re-laid once per unit into 4 byte-phase copies, transposed to
 //     [phase][word column][row]; after that every candidate reads ALIGNED 128-bit words and every
 //     VABSDIFF4 lane does algorithmic work (no pad byte, no per-use funnel shift).
-//   * thread = (macroblock, dx).  It keeps ND accumulators (all dy of the chunk) and, per word
+//   * thread = (macroblock, dx): at ND = 33 warp m holds dx 0..31 of macroblock m and one more warp dx = 32 of
+//     all macroblocks.  A thread keeps ND accumulators (all dy of the chunk) and, per word
 //     column, the BS macroblock words in registers; one LDS.128 delivers 4 window rows that feed
 //     up to 4*min(ND,BS) VABSDIFF4.U8.ACC -- ~33 ALU ops per shared-memory load at ND=33.
 //     Row padding RP = 16 (mod 32) words and phase stride PS = 4 (mod 32) words make the 16-byte
@@ -23,7 +25,7 @@
 //     is the first strict minimum in rows-outer/cols-inner scan order; threads reduce over their
 //     ND dy values in registers and across the macroblock with a shared-memory atomicMin.
 //   * wrap8 cost (the reference's metric): per word t = (r|H) - (c&~H); z = t ^ (~r&H) ^ (c&H);
-//     acc += bytesum(z)  (IADD + LOP3 + IDP.4A instead of one VABSDIFF4).
+//     acc += 64 * bytesum(z)  (IADD + LOP3 + IDP.4A instead of one VABSDIFF4; the factor 64 is the key scale).
 #pragma once
 #include <cuda.h>
 

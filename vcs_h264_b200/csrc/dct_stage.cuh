@@ -323,10 +323,10 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                         tk[c][k] = t.x; tk[c][k + 1] = t.y;
                     }
                 // All 8 chains first (one basic block: the DFMAs of different j interleave), then the quantiser.
-                // The rounded modes take q0 = D * RN(1/Q); a lane whose q0 comes within 2^-30 of a half-integer
-                // is re-done with the IEEE quotient in a rarely taken second pass.  The test is on the high word of
-                // |q0 - rint(q0)| (two integer instructions per index): >= 0x3FDFFFFF means |.| >= 0.5 - 2^-22, which
-                // includes every value within 2^-30 of a half-integer; the extra second passes are exact too.
+                // The rounded modes take q0 = D * RN(1/Q), within 2^-40 of the true quotient; a lane whose q0 comes within
+                // 2^-22 of a half-integer is re-done with the IEEE quotient in a rarely taken second pass.  The test is on
+                // the high word of |q0 - rint(q0)| (two integer instructions per index): >= 0x3FDFFFFF means
+                // |.| >= 0.5 - 2^-22, far wider than the 2^-40 that could flip a rounding; second passes are exact.
                 constexpr uint32_t NEAR_HALF_HI = 0x3FDFFFFFu;
                 double sj[DCT_NCH][8];
 #pragma unroll

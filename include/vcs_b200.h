@@ -227,6 +227,19 @@ int vcs_decode_clip_host(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_
 int vcs_count_nonzero_dev(vcs_ctx *ctx, int coef_mode, const void *coef, size_t n,
                           unsigned long long *count_host);
 
+/* ---- fp32 tier of the DCT stage (BASELINE.json north_star: "fp32 DCT reconstruction ... any coefficient that flips at
+ * a quantisation rounding boundary is counted and reported"; SURVEY appendix A, tier T2) ---------------------------- */
+/* bits = 64 (default): the transforms of DCTcompressor.py:111-121 in float64 with the reference's operation order,
+ * bit-identical.  bits = 32: the same kernel in float (FFMA), no exact-quotient fallback: results are close, not equal,
+ * and are judged with vcs_flip_counters_dev.  Applies to every later DCT-stage launch of this context (compress,
+ * decompress, encode/decode clip); the packed sink and the float64 coefficient planes stay with the exact tier. */
+int vcs_set_dct_precision(vcs_ctx *ctx, int bits);
+/* Compares two DEVICE results of the same shape: ncoef rounded indices (coef_mode VCS_COEF_I8_RINT or _I16_RINT) and
+ * npx uint8 pixels (either count may be 0).  out3_host[0] = indices that differ (rounding-boundary flips),
+ * [1] = pixels that differ (truncation-boundary flips, decoder.py:52-60), [2] = sum of squared pixel differences. */
+int vcs_flip_counters_dev(vcs_ctx *ctx, int coef_mode, const void *coef_a, const void *coef_b, size_t ncoef,
+                          const uint8_t *px_a, const uint8_t *px_b, size_t npx, unsigned long long *out3_host);
+
 /* ---- intra mode decision: IntraframeCompression/intraframe.py + intramodes.py --------- */
 /* luma4x4 (intraframe.py:24-151): 9 predictors per 4x4 block, first strict SAD minimum, neighbours from the
  * ORIGINAL plane.  Y: uint8 H x W (multiples of 4); res / pred: int32 H x W; modes: uint8 (H/4) x (W/4). */

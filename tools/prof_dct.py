@@ -1,11 +1,13 @@
-"""Run the residual/DCT stage alone on a 1080p clip with the bench's settings (int8 indices + reconstruction)."""
+"""Run the residual/DCT stage alone on a 1080p clip with the bench's settings (int8 indices + reconstruction).
+DCT_BITS=32 times the fp32 tier instead of the exact float64 one."""
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vcs_h264_b200 as v
 from vcs_h264_b200 import synth, _capi
 T, H, W = 60, 1080, 1920
 clip = torch.from_numpy(synth.clip(T, H, W, seed=1)).cuda()
-ce = v.ClipEncoder([H, W], block_size=16, search="full", search_range=16, gop_len=4, coef_mode=v.COEF_I8_RINT)
+ce = v.ClipEncoder([H, W], block_size=16, search="full", search_range=16, gop_len=4, coef_mode=v.COEF_I8_RINT,
+                   dct_precision=int(os.environ.get("DCT_BITS", "64")))
 out = ce.alloc_device_outputs(T)
 ce.encode_device(clip, out)
 torch.cuda.synchronize()

@@ -11,7 +11,7 @@ from .motion import MotionProcessor
 from .DCTcompressor import DCTCompressor
 from .encoder import Encoder
 from .decoder import Decoder
-from .clip import ClipDecoder, ClipEncoder, sparsity_device
+from .clip import ClipDecoder, ClipEncoder, flip_counters, sparsity_device
 
-__all__ = ["MotionProcessor", "DCTCompressor", "Encoder", "Decoder", "Frame", "ClipEncoder", "ClipDecoder", "sparsity_device",
+__all__ = ["MotionProcessor", "DCTCompressor", "Encoder", "Decoder", "Frame", "ClipEncoder", "ClipDecoder", "sparsity_device", "flip_counters",
            "VcsError", "_capi"]

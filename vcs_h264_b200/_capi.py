@@ -85,6 +85,8 @@ SIGNATURES = {
     "vcs_decode_clip_dev": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "vcs_decode_clip_host": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "vcs_count_nonzero_dev": (_i, [_vp, _i, _vp, _sz, C.POINTER(C.c_ulonglong)]),
+    "vcs_set_dct_precision": (_i, [_vp, _i]),
+    "vcs_flip_counters_dev": (_i, [_vp, _i, _vp, _vp, _sz, _vp, _vp, _sz, C.POINTER(C.c_ulonglong)]),
     "vcs_intra_luma4x4_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "vcs_intra_luma16x16_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "vcs_intra_chroma8x8_dev": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -27,7 +27,7 @@ class ClipEncoder:
 
     def __init__(self, shape, block_size=16, search="full", search_range=16, gop_len=4, qf=50.0,
                  metric=_capi.METRIC_WRAP8, static_thr=2000, coef_mode=_capi.COEF_I16_RINT,
-                 kernel=_capi.ME_AUTO, device=0):
+                 kernel=_capi.ME_AUTO, device=0, dct_precision=64):
         H, W = int(shape[0]), int(shape[1])
         if search == "reference":
             self.params = _capi.me_reference_params(H, W, block_size)
@@ -48,6 +48,10 @@ class ClipEncoder:
         self.ctx = acquire_context(device)
         self.Q = _capi.q_tables(qf)
         self.ctx.set_q(self.Q)
+        # 64: float64 transforms, bit-identical with the reference (default).  32: the fp32 tier -- close, not equal;
+        # compare with flip_counters().  Set on every construction: contexts are pooled.
+        self.dct_precision = int(dct_precision)
+        self.ctx.call("vcs_set_dct_precision", self.dct_precision)
 
     def close(self):
         ctx, self.ctx = getattr(self, "ctx", None), None
@@ -191,12 +195,14 @@ class ClipDecoder:
     """Decoder.reconstruct_video's per-frame arithmetic (decoder.py:23-69) for a whole clip: motion
     compensation from the ORIGINAL I-frames, dequantise, IDCT, truncating store, YCrCb->BGR, wrap add."""
 
-    def __init__(self, shape, block_size=16, gop_len=4, qf=50.0, coef_mode=_capi.COEF_I16_RINT, device=0):
+    def __init__(self, shape, block_size=16, gop_len=4, qf=50.0, coef_mode=_capi.COEF_I16_RINT, device=0, dct_precision=64):
         self.H, self.W, self.bs, self.gop_len = int(shape[0]), int(shape[1]), block_size, gop_len
         self.coef_mode, self.device = coef_mode, device
         self.ctx = acquire_context(device)         # own context, like ClipEncoder
         self.Q = _capi.q_tables(qf)
         self.ctx.set_q(self.Q)
+        self.dct_precision = int(dct_precision)
+        self.ctx.call("vcs_set_dct_precision", self.dct_precision)
 
     def close(self):
         ctx, self.ctx = getattr(self, "ctx", None), None
@@ -244,6 +250,20 @@ class ClipDecoder:
         finally:
             self.ctx.use_own_stream()
         return recon_dev
+
+
+def flip_counters(ctx, coef_mode, coef_a, coef_b, recon_a=None, recon_b=None):
+    """How two device results differ (the fp32 tier against the exact one): rounded indices that crossed a rounding
+    boundary, pixels that crossed a truncation boundary, and the PSNR of one reconstruction against the other."""
+    import ctypes as C
+    import math
+    out = (C.c_ulonglong * 3)()
+    npx = recon_a.numel() if recon_a is not None else 0
+    ctx.call("vcs_flip_counters_dev", coef_mode, _capi.ptr(coef_a), _capi.ptr(coef_b), coef_a.numel(),
+             _capi.ptr(recon_a) if npx else None, _capi.ptr(recon_b) if npx else None, npx, out)
+    mse = out[2] / npx if npx else 0.0
+    return {"indices": coef_a.numel(), "index_flips": int(out[0]), "pixels": npx, "pixel_flips": int(out[1]),
+            "psnr_db": (10.0 * math.log10(255.0 ** 2 / mse) if mse > 0 else float("inf")) if npx else None}
 
 
 def sparsity_device(ctx, coef_dev, coef_mode):

@@ -41,6 +41,28 @@
 namespace vcs {
 
 __constant__ double c_dct[64];  // _dctMatrix(), row-major, computed on the host with libm
+__constant__ float c_dctf[64];  // the same values rounded to float: the fp32 tier (T2) only
+
+// The transform arithmetic is written once over a real type R.  double = the exact tier (bit-identical with the reference,
+// the default everywhere); float = the fp32 tier of SURVEY appendix A (T2): same kernel, FFMA instead of DFMA, no
+// exact-quotient fallback -- its results are judged by tolerance and by counted flips (vcs_flip_counters_dev), never by equality.
+template <typename R> struct DctReal;
+template <> struct DctReal<double> {
+    typedef double2 R2;
+    static constexpr bool exact = true;
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double rnd(double x) { return rint(x); }
+    static __device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
+    static __device__ __forceinline__ double cst(int k) { return c_dct[k]; }
+};
+template <> struct DctReal<float> {
+    typedef float2 R2;
+    static constexpr bool exact = false;
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float rnd(float x) { return rintf(x); }
+    static __device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+    static __device__ __forceinline__ float cst(int k) { return c_dctf[k]; }
+};
 
 constexpr int DCT_TILE_W = 32;                        // pixels per warp tile row (4 blocks)
 constexpr int DCT_WARPS = 4;                          // warps per CTA, each with a private tile
@@ -52,8 +74,11 @@ constexpr int DCT_QS = 10;                            // row stride of the Q tab
 constexpr int DCT_QN = 3 * 8 * DCT_QS;                // doubles per table
 constexpr int DCT_X_DOUBLES = DCT_NCH * 8 * DCT_RS;   // per-warp transform tile [NCH][8][RS]
 constexpr int DCT_PLANE = 8 * DCT_TILE_W * 3;         // bytes of one 8 x 32 x 3 byte tile
-constexpr size_t DCT_WARP_BYTES = (size_t)DCT_X_DOUBLES * sizeof(double) + 3 * DCT_PLANE;
-constexpr size_t DCT_SMEM_BYTES = 2 * DCT_QN * sizeof(double) + DCT_WARPS * DCT_WARP_BYTES;
+template <typename R> struct DctSizes {
+    static constexpr size_t WARP_BYTES = (size_t)DCT_X_DOUBLES * sizeof(R) + 3 * DCT_PLANE;   // transform tile + 3 byte tiles
+    static constexpr size_t SMEM_BYTES = 2 * DCT_QN * sizeof(R) + DCT_WARPS * WARP_BYTES;
+};
+constexpr size_t DCT_SMEM_BYTES = DctSizes<double>::SMEM_BYTES;
 
 struct DctArgs {
     int H, W;
@@ -123,24 +148,26 @@ enum { DCT_FWD = 0, DCT_FWD_INV = 1, DCT_FWD_INV_NOCOEF = 2, DCT_INV = 3 };
 #endif
 // (A full-width specialisation that drops the partial-tile predicates was tried: without the branches ptxas merges the
 // stages into one block, hoists loads across them and spills -- 104 bytes of stack at 80 registers.  Not kept.)
-template <int CM, int PATH>
+template <int CM, int PATH, typename R = double>
 __global__ void __launch_bounds__(DCT_THREADS, DCT_NCH == 1 ? (PATH == DCT_FWD ? VCS_DCT_MINB_FWD : VCS_DCT_MINB) : 4)
 dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
+    typedef DctReal<R> RT;
+    typedef typename RT::R2 R2;
     constexpr bool forward = PATH != DCT_INV, do_inverse = PATH != DCT_FWD, has_coef = PATH != DCT_FWD_INV_NOCOEF;
     constexpr int coef_mode = CM;
     extern __shared__ __align__(16) unsigned char dct_smem[];
-    double *s_q = reinterpret_cast<double *>(dct_smem);          // Q [3][64]
-    double *s_rq = s_q + DCT_QN;                                 // RN(1/Q)
+    R *s_q = reinterpret_cast<R *>(dct_smem);                    // Q [3][8][QS]
+    R *s_rq = s_q + DCT_QN;                                      // RN(1/Q)
     // lane and the warp's shared-memory offset are pinned in registers (the empty asm makes them opaque): ptxas otherwise
     // re-derives them from %tid at every use, 19 S2R + 50 integer instructions per tile
     int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint32_t wofs = (uint32_t)(2 * DCT_QN * sizeof(double)) + (uint32_t)warp * (uint32_t)DCT_WARP_BYTES;
+    uint32_t wofs = (uint32_t)(2 * DCT_QN * sizeof(R)) + (uint32_t)warp * (uint32_t)DctSizes<R>::WARP_BYTES;
     asm volatile("" : "+r"(lane));
     asm volatile("" : "+r"(wofs));
     unsigned char *wbase = dct_smem + wofs;
-    double *s_x = reinterpret_cast<double *>(wbase);                              // [3][8][RS]
-    uint8_t *s_pred = wbase + DCT_X_DOUBLES * sizeof(double);                     // [8][32*3] prediction (BGR)
+    R *s_x = reinterpret_cast<R *>(wbase);                                        // [NCH][8][RS]
+    uint8_t *s_pred = wbase + DCT_X_DOUBLES * sizeof(R);                          // [8][32*3] prediction (BGR)
     int8_t *s_in8 = reinterpret_cast<int8_t *>(s_pred + DCT_PLANE);               // [3][8][32] YCrCb-128
     uint8_t *s_out = reinterpret_cast<uint8_t *>(s_in8 + DCT_PLANE);              // [3][8][32] decoded YCrCb
 
@@ -153,8 +180,8 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     for (int k = threadIdx.x; k < 192; k += DCT_THREADS) {
         const double q = a.Q[k];
         const int ch = k >> 6, i = (k >> 3) & 7, j = k & 7;
-        s_q[(ch * 8 + i) * DCT_QS + j] = q;
-        s_rq[(ch * 8 + i) * DCT_QS + j] = 1.0 / q;
+        s_q[(ch * 8 + i) * DCT_QS + j] = (R)q;
+        s_rq[(ch * 8 + i) * DCT_QS + j] = (R)(1.0 / q);
     }
     __syncthreads();   // the only CTA-wide barrier
 
@@ -183,8 +210,8 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
     }
     // Row 0 of the DCT matrix is the single value 1/sqrt(8) (vcs_dct_matrix, like _dctMatrix()): it lives in a register, which
     // saves the constant fetches of one chain in 8 in every pass.
-    double a0 = c_dct[0];
-    asm volatile("" : "+d"(a0));
+    R a0 = RT::cst(0);
+    if constexpr (RT::exact) asm volatile("" : "+d"(a0)); else asm volatile("" : "+f"(a0));
     int p_have = -1;
     const uint8_t *cur = nullptr, *ref = nullptr;
     for (unsigned item = first; item < nitems; item += nwarps, p += (int)step_p, ty += step_ty, tx += step_tx) {
@@ -252,9 +279,9 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                 uint32_t yv[2] = {0, 0}, crv[2] = {0, 0}, cbv[2] = {0, 0};
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int B = byte_of(rw, 3 * u), G = byte_of(rw, 3 * u + 1), R = byte_of(rw, 3 * u + 2);
+                    const int pb = byte_of(rw, 3 * u), pg = byte_of(rw, 3 * u + 1), pr = byte_of(rw, 3 * u + 2);
                     int Y, Cr, Cb;
-                    bgr2ycrcb(B, G, R, Y, Cr, Cb);
+                    bgr2ycrcb(pb, pg, pr, Y, Cr, Cb);
                     yv[u >> 2] = put_byte(yv[u >> 2], (uint32_t)Y, u & 3);
                     crv[u >> 2] = put_byte(crv[u >> 2], (uint32_t)Cr, u & 3);
                     cbv[u >> 2] = put_byte(cbv[u >> 2], (uint32_t)Cb, u & 3);
@@ -288,21 +315,21 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
         if (forward) {
             // ---- B: column pass  T = C . X  (T[i][j] = sum_k C[i][k] X[k][j]) -------------------------------
             if (col_on) {
-                double xk[DCT_NCH][8];
+                R xk[DCT_NCH][8];
 #pragma unroll
                 for (int c = 0; c < DCT_NCH; ++c)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) xk[c][k] = (double)(int)s_in8[((ch0 + c) * 8 + k) * DCT_TILE_W + lane];
+                    for (int k = 0; k < 8; ++k) xk[c][k] = (R)(int)s_in8[((ch0 + c) * 8 + k) * DCT_TILE_W + lane];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    double s[DCT_NCH];
+                    R s[DCT_NCH];
 #pragma unroll
-                    for (int c = 0; c < DCT_NCH; ++c) s[c] = 0.0;
+                    for (int c = 0; c < DCT_NCH; ++c) s[c] = (R)0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double cc = i == 0 ? a0 : c_dct[i * 8 + k];
+                        const R cc = i == 0 ? a0 : RT::cst(i * 8 + k);
 #pragma unroll
-                        for (int c = 0; c < DCT_NCH; ++c) s[c] = __fma_rn(cc, xk[c][k], s[c]);
+                        for (int c = 0; c < DCT_NCH; ++c) s[c] = RT::fma(cc, xk[c][k], s[c]);
                     }
 #pragma unroll
                     for (int c = 0; c < DCT_NCH; ++c) s_x[(c * 8 + i) * DCT_RS + lane] = s[c];
@@ -314,12 +341,12 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
 #pragma unroll
             for (int c = 0; c < DCT_NCH; ++c) nnz_lane[c] = 0;
             if (row_on) {
-                double tk[DCT_NCH][8];
+                R tk[DCT_NCH][8];
 #pragma unroll
                 for (int c = 0; c < DCT_NCH; ++c)
 #pragma unroll
                     for (int k = 0; k < 8; k += 2) {
-                        const double2 t = *reinterpret_cast<const double2 *>(s_x + c * 8 * DCT_RS + rbase0 + k);
+                        const R2 t = *reinterpret_cast<const R2 *>(s_x + c * 8 * DCT_RS + rbase0 + k);
                         tk[c][k] = t.x; tk[c][k + 1] = t.y;
                     }
                 // All 8 chains first (one basic block: the DFMAs of different j interleave), then the quantiser.
@@ -328,44 +355,46 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                 // the high word of |q0 - rint(q0)| (two integer instructions per index): >= 0x3FDFFFFF means
                 // |.| >= 0.5 - 2^-22, far wider than the 2^-40 that could flip a rounding; second passes are exact.
                 constexpr uint32_t NEAR_HALF_HI = 0x3FDFFFFFu;
-                double sj[DCT_NCH][8];
+                R sj[DCT_NCH][8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
 #pragma unroll
-                    for (int c = 0; c < DCT_NCH; ++c) sj[c][j] = 0.0;
+                    for (int c = 0; c < DCT_NCH; ++c) sj[c][j] = (R)0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double cc = j == 0 ? a0 : c_dct[j * 8 + k];
+                        const R cc = j == 0 ? a0 : RT::cst(j * 8 + k);
 #pragma unroll
-                        for (int c = 0; c < DCT_NCH; ++c) sj[c][j] = __fma_rn(tk[c][k], cc, sj[c][j]);
+                        for (int c = 0; c < DCT_NCH; ++c) sj[c][j] = RT::fma(tk[c][k], cc, sj[c][j]);
                     }
                 }
 #pragma unroll
                 for (int c = 0; c < DCT_NCH; ++c) {
                     const int ch = ch0 + c;
-                    bool exact = coef_mode == 0;        // un-rounded mode: np.true_divide (DCTcompressor.py:71)
+                    bool exact = coef_mode == 0 || !RT::exact;   // un-rounded mode: np.true_divide (DCTcompressor.py:71); fp32 tier: no second pass
                     uint32_t pk[4];
 #pragma unroll 1
                     for (int attempt = 0; attempt < 2; ++attempt) {
                         uint32_t far = 0;               // max over the row of the high word of |q0 - rint(q0)|
-                        double dprev = 0.0, eprev = 0.0;
-                        double2 Q2 = make_double2(0.0, 0.0), rq2 = make_double2(0.0, 0.0);
+                        R dprev = (R)0, eprev = (R)0;
+                        R2 Q2 = RT::mk2((R)0, (R)0), rq2 = RT::mk2((R)0, (R)0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             if ((j & 1) == 0) {
-                                Q2 = *reinterpret_cast<const double2 *>(s_q + (ch * 8 + rp_i) * DCT_QS + j);
-                                if (coef_mode != 0) rq2 = *reinterpret_cast<const double2 *>(s_rq + (ch * 8 + rp_i) * DCT_QS + j);
+                                Q2 = *reinterpret_cast<const R2 *>(s_q + (ch * 8 + rp_i) * DCT_QS + j);
+                                if (coef_mode != 0) rq2 = *reinterpret_cast<const R2 *>(s_rq + (ch * 8 + rp_i) * DCT_QS + j);
                             }
-                            const double Q = (j & 1) ? Q2.y : Q2.x;
-                            double v;
+                            const R Q = (j & 1) ? Q2.y : Q2.x;
+                            R v;
                             if (coef_mode == 0) {
                                 v = sj[c][j] / Q;
+                            } else if (!RT::exact) {
+                                v = RT::rnd(sj[c][j] * ((j & 1) ? rq2.y : rq2.x));   // fp32 tier: one multiply, flips are counted, not prevented
                             } else if (!exact) {
-                                const double q0 = sj[c][j] * ((j & 1) ? rq2.y : rq2.x);
-                                v = rint(q0);                              // np.round (dct.py:179) of RN(s/Q)
-                                far = max(far, (uint32_t)__double2hiint(q0 - v) & 0x7fffffffu);
+                                const R q0 = sj[c][j] * ((j & 1) ? rq2.y : rq2.x);
+                                v = RT::rnd(q0);                           // np.round (dct.py:179) of RN(s/Q)
+                                if constexpr (RT::exact) far = max(far, (uint32_t)__double2hiint(q0 - v) & 0x7fffffffu);
                             } else {
-                                v = rint(sj[c][j] / Q);                    // the exact quotient decides
+                                v = RT::rnd(sj[c][j] / Q);                 // the exact quotient decides
                             }
                             if (has_coef) {
                                 if (coef_mode == 2) {
@@ -374,13 +403,13 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                                     pk[j >> 2] = put_byte(pk[j >> 2], (uint32_t)(int)v, j & 3);
                                 } else if (j & 1) {
                                     *reinterpret_cast<double2 *>(reinterpret_cast<double *>(cptr) + j - 1) =
-                                        make_double2(dprev, v);
+                                        make_double2((double)dprev, (double)v);
                                 } else {
                                     dprev = v;
                                 }
                             }
                             if (do_inverse) {                                           // E = blk * Q (DCTcompressor.py:86)
-                                if (j & 1) *reinterpret_cast<double2 *>(s_x + c * 8 * DCT_RS + rbase0 + j - 1) = make_double2(eprev, v * Q);
+                                if (j & 1) *reinterpret_cast<R2 *>(s_x + c * 8 * DCT_RS + rbase0 + j - 1) = RT::mk2(eprev, v * Q);
                                 else eprev = v * Q;
                             }
                         }
@@ -422,22 +451,22 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
 #pragma unroll
             for (int c = 0; c < DCT_NCH; ++c) {
                 const int ch = ch0 + c;
-                double qv[8];
+                R qv[8];
                 if (coef_mode == 2) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(cptr);
                     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) qv[j] = (double)(int)(int16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
+                    for (int j = 0; j < 8; ++j) qv[j] = (R)(int)(int16_t)((w[j >> 1] >> (16 * (j & 1))) & 0xffff);
                 } else if (coef_mode == 3) {
                     const uint2 v = *reinterpret_cast<const uint2 *>(cptr);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) qv[j] = (double)(int)(int8_t)(((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xff);
+                    for (int j = 0; j < 8; ++j) qv[j] = (R)(int)(int8_t)(((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xff);
                 } else {
                     const double *o = reinterpret_cast<const double *>(cptr);
 #pragma unroll
                     for (int j = 0; j < 8; j += 2) {
                         const double2 v = *reinterpret_cast<const double2 *>(o + j);
-                        qv[j] = v.x; qv[j + 1] = v.y;
+                        qv[j] = (R)v.x; qv[j + 1] = (R)v.y;
                     }
                 }
 #pragma unroll
@@ -448,21 +477,21 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
             __syncwarp();
             // ---- D: inverse column pass  T' = C^T . E  (T'[i][j] = sum_k C[k][i] E[k][j]) ---------------------
             if (col_on) {
-                double ek[DCT_NCH][8];
+                R ek[DCT_NCH][8];
 #pragma unroll
                 for (int c = 0; c < DCT_NCH; ++c)
 #pragma unroll
                     for (int k = 0; k < 8; ++k) ek[c][k] = s_x[(c * 8 + k) * DCT_RS + lane];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    double s[DCT_NCH];
+                    R s[DCT_NCH];
 #pragma unroll
-                    for (int c = 0; c < DCT_NCH; ++c) s[c] = 0.0;
+                    for (int c = 0; c < DCT_NCH; ++c) s[c] = (R)0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double cc = k == 0 ? a0 : c_dct[k * 8 + i];
+                        const R cc = k == 0 ? a0 : RT::cst(k * 8 + i);
 #pragma unroll
-                        for (int c = 0; c < DCT_NCH; ++c) s[c] = __fma_rn(cc, ek[c][k], s[c]);
+                        for (int c = 0; c < DCT_NCH; ++c) s[c] = RT::fma(cc, ek[c][k], s[c]);
                     }
 #pragma unroll
                     for (int c = 0; c < DCT_NCH; ++c) s_x[(c * 8 + i) * DCT_RS + lane] = s[c];
@@ -471,12 +500,12 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
             __syncwarp();
             // ---- E: inverse row pass  P = T' . C ; truncating uint8 store ; +128 ---------------------------------
             if (row_on) {
-                double tk[DCT_NCH][8];
+                R tk[DCT_NCH][8];
 #pragma unroll
                 for (int c = 0; c < DCT_NCH; ++c)
 #pragma unroll
                     for (int k = 0; k < 8; k += 2) {
-                        const double2 t = *reinterpret_cast<const double2 *>(s_x + c * 8 * DCT_RS + rbase0 + k);
+                        const R2 t = *reinterpret_cast<const R2 *>(s_x + c * 8 * DCT_RS + rbase0 + k);
                         tk[c][k] = t.x; tk[c][k + 1] = t.y;
                     }
                 uint32_t w[DCT_NCH][2];
@@ -484,14 +513,14 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
                 for (int c = 0; c < DCT_NCH; ++c) w[c][0] = w[c][1] = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    double s[DCT_NCH];
+                    R s[DCT_NCH];
 #pragma unroll
-                    for (int c = 0; c < DCT_NCH; ++c) s[c] = 0.0;
+                    for (int c = 0; c < DCT_NCH; ++c) s[c] = (R)0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const double cc = k == 0 ? a0 : c_dct[k * 8 + j];
+                        const R cc = k == 0 ? a0 : RT::cst(k * 8 + j);
 #pragma unroll
-                        for (int c = 0; c < DCT_NCH; ++c) s[c] = __fma_rn(tk[c][k], cc, s[c]);
+                        for (int c = 0; c < DCT_NCH; ++c) s[c] = RT::fma(tk[c][k], cc, s[c]);
                     }
                     // float64 -> uint8 store (DCTcompressor.py:81,88): truncate toward zero, low 8 bits; then +128
 #pragma unroll
@@ -520,11 +549,11 @@ dct_stage_kernel(const __grid_constant__ DctArgs a, int nP) {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int Y = byte_of(yw, u), Cr = byte_of(crw, u), Cb = byte_of(cbw, u);
-                    int B, G, R;
-                    ycrcb2bgr(Y, Cr, Cb, B, G, R);
-                    ow[(3 * u) >> 2] = put_byte(ow[(3 * u) >> 2], (uint32_t)B, (3 * u) & 3);
-                    ow[(3 * u + 1) >> 2] = put_byte(ow[(3 * u + 1) >> 2], (uint32_t)G, (3 * u + 1) & 3);
-                    ow[(3 * u + 2) >> 2] = put_byte(ow[(3 * u + 2) >> 2], (uint32_t)R, (3 * u + 2) & 3);
+                    int pb, pg, pr;
+                    ycrcb2bgr(Y, Cr, Cb, pb, pg, pr);
+                    ow[(3 * u) >> 2] = put_byte(ow[(3 * u) >> 2], (uint32_t)pb, (3 * u) & 3);
+                    ow[(3 * u + 1) >> 2] = put_byte(ow[(3 * u + 1) >> 2], (uint32_t)pg, (3 * u + 1) & 3);
+                    ow[(3 * u + 2) >> 2] = put_byte(ow[(3 * u + 2) >> 2], (uint32_t)pr, (3 * u + 2) & 3);
                 }
                 uint32_t ov[6];   // pred + decoded, uint8 wrap (decoder.py:57)
 #pragma unroll
@@ -602,6 +631,26 @@ __global__ void count_nonzero_kernel(const void *__restrict__ coef, size_t n, un
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) c += shfl_xor_u64(c, m);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// Flip counters of the fp32 tier: how many elements of two equally shaped arrays differ
+// (rounded indices that crossed a rounding boundary, pixels that crossed a truncation boundary) and, for pixels, the sum
+// of squared differences (PSNR of one against the other).
+template <typename E>
+__global__ void flip_count_kernel(const E *__restrict__ x, const E *__restrict__ y, size_t n, unsigned long long *__restrict__ flips,
+                                  unsigned long long *__restrict__ sse) {
+    unsigned long long f = 0, q = 0;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const int d = (int)x[k] - (int)y[k];
+        f += d != 0;
+        q += (unsigned long long)(d * d);
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) { f += shfl_xor_u64(f, m); q += shfl_xor_u64(q, m); }
+    if ((threadIdx.x & 31) == 0) {
+        if (f) atomicAdd(flips, f);
+        if (sse && q) atomicAdd(sse, q);
+    }
 }
 
 // get_residuals (motion.py:38-40) / _fully_reconstruct (decoder.py:57): byte-wise wrap, 16 bytes per thread

@@ -50,7 +50,8 @@ struct vcs_ctx {
     double *d_Q = nullptr;
     int64_t launches = 0;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
-    int dct_occupancy[4][4] = {{0}};   // [coef_mode][path], filled on first use
+    int dct_occupancy[2][4][4] = {{{0}}};   // [fp32 tier][coef_mode][path], filled on first use
+    int dct_fp32 = 0;                  // vcs_set_dct_precision: 0 = float64 exact (default), 1 = fp32 tier
     size_t smem_optin = 0;
     void *dev[NUM_DEV_SLOTS] = {nullptr};
     size_t dev_cap[NUM_DEV_SLOTS] = {0};
@@ -231,13 +232,17 @@ int launch_dct(vcs_ctx *ctx, cudaStream_t st, DctArgs &a, int nP) {
     if (!a.forward && !a.coef) return fail(ctx, VCS_E_INVALID, "inverse pass without coefficients");
     const int path = !a.forward ? DCT_INV : (!inv ? DCT_FWD : (a.coef ? DCT_FWD_INV : DCT_FWD_INV_NOCOEF));
     typedef void (*dct_fn)(const DctArgs, int);
-#define VCS_DCT_ROW(CM) {dct_stage_kernel<CM, 0>, dct_stage_kernel<CM, 1>, dct_stage_kernel<CM, 2>, dct_stage_kernel<CM, 3>}
-    static const dct_fn table[4][4] = {VCS_DCT_ROW(0), VCS_DCT_ROW(1), VCS_DCT_ROW(2), VCS_DCT_ROW(3)};
+#define VCS_DCT_ROW(CM, R) {dct_stage_kernel<CM, 0, R>, dct_stage_kernel<CM, 1, R>, dct_stage_kernel<CM, 2, R>, dct_stage_kernel<CM, 3, R>}
+    static const dct_fn table[2][4][4] = {{VCS_DCT_ROW(0, double), VCS_DCT_ROW(1, double), VCS_DCT_ROW(2, double), VCS_DCT_ROW(3, double)},
+                                          {VCS_DCT_ROW(0, float), VCS_DCT_ROW(1, float), VCS_DCT_ROW(2, float), VCS_DCT_ROW(3, float)}};
 #undef VCS_DCT_ROW
-    const dct_fn kern = table[a.coef_mode][path];
-    int &occ = ctx->dct_occupancy[a.coef_mode][path];
+    const int f32 = ctx->dct_fp32 ? 1 : 0;
+    if (f32 && a.bitmap) return fail(ctx, VCS_E_INVALID, "the packed sink belongs to the exact tier");
+    const size_t smem_bytes = f32 ? DctSizes<float>::SMEM_BYTES : DctSizes<double>::SMEM_BYTES;
+    const dct_fn kern = table[f32][a.coef_mode][path];
+    int &occ = ctx->dct_occupancy[f32][a.coef_mode][path];
     if (occ == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DCT_THREADS, DCT_SMEM_BYTES) != cudaSuccess || occ < 1) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DCT_THREADS, smem_bytes) != cudaSuccess || occ < 1) {
             occ = 0;
             return fail(ctx, VCS_E_CUDA, "dct_stage_kernel does not fit an SM");
         }
@@ -249,7 +254,7 @@ int launch_dct(vcs_ctx *ctx, cudaStream_t st, DctArgs &a, int nP) {
     if (nitems >= (1ll << 31)) return fail(ctx, VCS_E_INVALID, "too many 8x32 tiles in one launch (%lld)", nitems);
     long long grid = (long long)ctx->sm_count * occ;   // exactly one resident wave
     if (grid * DCT_WARPS > nitems) grid = (nitems + DCT_WARPS - 1) / DCT_WARPS;
-    kern<<<(unsigned)grid, DCT_THREADS, DCT_SMEM_BYTES, st>>>(a, nP);
+    kern<<<(unsigned)grid, DCT_THREADS, smem_bytes, st>>>(a, nP);
     CK(ctx, cudaGetLastError());
     ctx->launches += 1;
     return VCS_OK;
@@ -498,7 +503,9 @@ int vcs_create(int device, vcs_ctx **out) {
     ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     double C[64];
+    float Cf[64];
     vcs_dct_matrix(C);
+    for (int k = 0; k < 64; ++k) Cf[k] = (float)C[k];
     static_assert(DCT_SMEM_BYTES <= 48 * 1024, "dct_stage_kernel relies on the default shared-memory limit");
     vcs_q_tables(50.0, ctx->h_Q);  // DCTcompressor.py:29 QF = 50
     int prio_lo = 0, prio_hi = 0;
@@ -512,6 +519,7 @@ int vcs_create(int device, vcs_ctx **out) {
         cudaMalloc(&ctx->d_Q, sizeof(ctx->h_Q)) != cudaSuccess ||
         cudaHostAlloc((void **)&ctx->h_errflag, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaMemcpyToSymbol(c_dct, C, sizeof(C)) != cudaSuccess ||
+        cudaMemcpyToSymbol(c_dctf, Cf, sizeof(Cf)) != cudaSuccess ||
         cudaMemcpy(ctx->d_Q, ctx->h_Q, sizeof(ctx->h_Q), cudaMemcpyHostToDevice) != cudaSuccess) {
         vcs_destroy(ctx);
         return VCS_E_CUDA;
@@ -856,6 +864,41 @@ int vcs_count_nonzero_dev(vcs_ctx *ctx, int coef_mode, const void *coef, size_t 
         ctx->launches += 1;
     }
     CK(ctx, cudaMemcpyAsync(count_host, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    return VCS_OK;
+}
+
+int vcs_set_dct_precision(vcs_ctx *ctx, int bits) {
+    VCS_ENTER(ctx);
+    if (bits != 32 && bits != 64) return fail(ctx, VCS_E_INVALID, "DCT precision is 64 (exact tier) or 32 (fp32 tier), not %d", bits);
+    ctx->dct_fp32 = bits == 32;
+    return VCS_OK;
+}
+
+int vcs_flip_counters_dev(vcs_ctx *ctx, int coef_mode, const void *coef_a, const void *coef_b, size_t ncoef,
+                          const uint8_t *px_a, const uint8_t *px_b, size_t npx, unsigned long long *out3_host) {
+    VCS_ENTER(ctx);
+    if (!out3_host || (coef_mode != VCS_COEF_I8_RINT && coef_mode != VCS_COEF_I16_RINT) || (ncoef && (!coef_a || !coef_b)) ||
+        (npx && (!px_a || !px_b)))
+        return fail(ctx, VCS_E_INVALID, "bad arguments (flip counters compare int8 or int16 index planes and uint8 frames)");
+    unsigned long long *d_cnt; int rc;
+    if ((rc = dev_buf(ctx, S_CYC, 24, (void **)&d_cnt))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx, cudaMemsetAsync(d_cnt, 0, 24, st));
+    const int cap = ctx->sm_count * 8;
+    if (ncoef) {
+        int blocks = (int)((ncoef + 1023) / 1024);
+        if (coef_mode == VCS_COEF_I8_RINT) flip_count_kernel<int8_t><<<blocks < cap ? blocks : cap, 256, 0, st>>>((const int8_t *)coef_a, (const int8_t *)coef_b, ncoef, d_cnt, nullptr);
+        else flip_count_kernel<int16_t><<<blocks < cap ? blocks : cap, 256, 0, st>>>((const int16_t *)coef_a, (const int16_t *)coef_b, ncoef, d_cnt, nullptr);
+        ctx->launches += 1;
+    }
+    if (npx) {
+        int blocks = (int)((npx + 1023) / 1024);
+        flip_count_kernel<uint8_t><<<blocks < cap ? blocks : cap, 256, 0, st>>>(px_a, px_b, npx, d_cnt + 1, d_cnt + 2);
+        ctx->launches += 1;
+    }
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaMemcpyAsync(out3_host, d_cnt, 24, cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaStreamSynchronize(st));
     return VCS_OK;
 }

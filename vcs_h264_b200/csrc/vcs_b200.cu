@@ -293,8 +293,7 @@ int encode_dev(vcs_ctx *ctx, cudaStream_t st, const vcs_me_params *p, const Fram
         st = st2;
     }
     if (coef || recon) {
-        DctArgs a;
-        memset(&a, 0, sizeof(a));
+        DctArgs a{};
         a.H = p->H; a.W = p->W; a.fa = fa; a.has_fa = 1; a.mv = mv; a.bs = p->bs;
         a.nbx = p->W / p->bs; a.nby = p->H / p->bs; a.forward = 1; a.inverse = recon != nullptr;
         a.coef_mode = coef_mode; a.coef = coef; a.recon = recon;
@@ -710,8 +709,7 @@ int vcs_add_wrap_host(vcs_ctx *c, const uint8_t *a, const uint8_t *b, size_t n, 
 int vcs_compress_dev(vcs_ctx *ctx, int H, int W, const uint8_t *bgr, int coef_mode, void *coef) {
     VCS_ENTER(ctx);
     if (!bgr || !coef) return fail(ctx, VCS_E_INVALID, "NULL argument");
-    DctArgs a;
-    memset(&a, 0, sizeof(a));
+    DctArgs a{};
     a.H = H; a.W = W; a.img = bgr; a.bs = 8; a.forward = 1; a.coef_mode = coef_mode; a.coef = coef;
     return launch_dct(ctx, ctx->stream, a, 1);
 }
@@ -737,8 +735,7 @@ int vcs_decompress_dev(vcs_ctx *ctx, int H, int W, int coef_mode, const void *co
                        uint8_t *bgr) {
     VCS_ENTER(ctx);
     if (!coef || !bgr) return fail(ctx, VCS_E_INVALID, "NULL argument");
-    DctArgs a;
-    memset(&a, 0, sizeof(a));
+    DctArgs a{};
     a.H = H; a.W = W; a.bs = 8; a.forward = 0; a.inverse = 1; a.coef_mode = coef_mode;
     a.coef = const_cast<void *>(coef); a.pred_in = pred; a.recon = bgr;
     return launch_dct(ctx, ctx->stream, a, 1);
@@ -790,8 +787,7 @@ int vcs_residual_dct_clip_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t 
     VCS_ENTER(ctx);
     if (!frames || !mv || gop_len < 2 || T < 1 || bs <= 0 || H < bs || W < bs)
         return fail(ctx, VCS_E_INVALID, "bad clip arguments");
-    DctArgs a;
-    memset(&a, 0, sizeof(a));
+    DctArgs a{};
     a.H = H; a.W = W; a.fa = clip_addr(frames, H, W, gop_len); a.has_fa = 1; a.mv = mv; a.bs = bs;
     a.nbx = W / bs; a.nby = H / bs; a.forward = 1; a.inverse = recon != nullptr;
     a.coef_mode = coef_mode; a.coef = coef; a.recon = recon;
@@ -806,8 +802,7 @@ int vcs_decode_clip_dev(vcs_ctx *ctx, int H, int W, int bs, const uint8_t *ref_f
     if (!ref_frames || !mv || !coef || !recon || gop_len < 2 || T < 1 || bs <= 0 || H < bs || W < bs)
         return fail(ctx, VCS_E_INVALID, "bad decode arguments");
     const long long fs = (long long)H * W * 3;
-    DctArgs a;
-    memset(&a, 0, sizeof(a));
+    DctArgs a{};
     a.H = H; a.W = W; a.has_fa = 1; a.mv = mv; a.bs = bs; a.nbx = W / bs; a.nby = H / bs;
     a.fa.cur_base = ref_frames; a.fa.ref_base = ref_frames;      // only the I-frames are given: [nG][H][W][3]
     a.fa.cur_gop_stride = fs; a.fa.cur_frame_stride = 0; a.fa.ref_gop_stride = fs; a.fa.ppg = gop_len - 1;

@@ -30,6 +30,46 @@ def test_library_exports_every_declared_symbol(capi):
     assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
 
 
+def test_ctypes_signatures_follow_the_header(capi):
+    """Every prototype of include/vcs_b200.h against its ctypes binding: same number of parameters, and pointers /
+    integers / doubles / 64-bit sizes in the same places (a drifted binding would pass garbage through the C ABI)."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, "include", "vcs_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\b([a-z_A-Z0-9 ]+?[ \*]+)(vcs_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr)
+    assert len(protos) >= 30
+
+    def kind_of_c(decl):
+        decl = decl.strip()
+        if "*" in decl or "[" in decl:
+            return "ptr"
+        base = re.sub(r"\b(const|unsigned|signed)\b", "", decl).split()
+        t = base[0] if base else "int"
+        if t == "double":
+            return "f64"
+        if t in ("size_t", "int64_t", "uint64_t") or decl.startswith("unsigned long long") or decl.startswith("long long"):
+            return "i64"
+        return "i32"
+
+    def kind_of_ctypes(t):
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        if t is C.c_double:
+            return "f64"
+        return "i64" if C.sizeof(t) == 8 else "i32"
+
+    seen = set()
+    for ret, name, params in protos:
+        seen.add(name)
+        plist = [q for q in (x.strip() for x in params.split(",")) if q and q != "void"]
+        res, args = capi.SIGNATURES[name]
+        assert len(plist) == len(args), (name, plist, args)
+        for decl, t in zip(plist, args):
+            assert kind_of_c(decl) == kind_of_ctypes(t), (name, decl, t)
+        assert kind_of_c(ret + "x") == kind_of_ctypes(res), (name, ret, res)
+    assert seen == set(capi.SIGNATURES)
+
+
 def test_no_cpu_fallback(capi):
     import torch
     if torch.cuda.is_available():
